@@ -1,0 +1,188 @@
+"""Host-side logic of the drop-in: directions, k-space, group rules, the SED container.
+Mirrors the reference's own unit tests (tests/test_helpers.py, test_sed.py, test_trajectory.py)
+and pins k-paths / k-grids / lattice vectors against the real reference's outputs (tests/golden)."""
+import numpy as np
+import pytest
+
+from psa_b200 import SED, Trajectory, parse_direction
+from psa_b200 import groups as G
+from psa_b200 import kspace
+
+S2, S3 = 1 / np.sqrt(2), 1 / np.sqrt(3)
+
+
+@pytest.mark.parametrize("spec,expected", [
+    ("x", [1, 0, 0]), ("y", [0, 1, 0]), ("z", [0, 0, 1]), ("100", [1, 0, 0]),
+    ("xy", [S2, S2, 0]), ("110", [S2, S2, 0]), ("xyz", [S3, S3, S3]), ("111", [S3, S3, S3]),
+    ("0,1,0", [0, 1, 0]), (" 1 0 0 ", [1, 0, 0]),
+    (0, [1, 0, 0]), (90, [0, 1, 0]), (45, [S2, S2, 0]), ("180.0", [-1, 0, 0]),
+    ([1, 0, 0], [1, 0, 0]), ((0, 5, 0), [0, 1, 0]), (np.array([1, 1, 1]), [S3, S3, S3]),
+    ([45], [S2, S2, 0]), (np.array(60.0), [0.5, np.sqrt(3) / 2, 0]),
+    ({"angle": 30}, [np.sqrt(3) / 2, 0.5, 0]), ({"h": 1, "k": 0, "l": 0}, [1, 0, 0]),
+    ({"h": 1, "k": 1, "l": 0}, [S2, S2, 0]), ({"h": 0, "k": 0, "l": 2}, [0, 0, 1]),
+])
+def test_parse_direction(spec, expected):
+    out = parse_direction(spec)
+    assert out.dtype == np.float32
+    np.testing.assert_allclose(out, np.array(expected, np.float32), atol=1e-6)
+
+
+@pytest.mark.parametrize("bad", ["invalid_string", [1, 2], [1, 2, 3, 4], np.array([[1, 0, 0], [0, 1, 0]]),
+                                 {"a": 1, "b": 2}, [0, 0, 0], np.array([1e-8, 1e-9, 1e-10], np.float32)])
+def test_parse_direction_invalid(bad):
+    with pytest.raises(ValueError):
+        parse_direction(bad)
+
+
+def test_parse_direction_type_error():
+    with pytest.raises(TypeError, match="Unsupported direction type: <class 'NoneType'>"):
+        parse_direction(None)
+
+
+def test_lattice_and_kpaths_match_reference(gold_si):
+    g = gold_si
+    lat = kspace.Lattice.from_box(g["box_matrix"], *g["cells"])
+    np.testing.assert_array_equal(lat.recip_vecs_prim, g["recip_vecs_prim"])
+    np.testing.assert_array_equal(lat.a1, g["a1"])
+    np.testing.assert_array_equal(lat.b1, g["b1"])
+    for tag, d in (("100", [1, 0, 0]), ("110", [1, 1, 0]), ("111", "111")):
+        mags, vecs = kspace.k_path(lat, d, 4.0, 12)
+        np.testing.assert_array_equal(mags, g[f"kpath_{tag}_mags"])
+        np.testing.assert_array_equal(vecs, g[f"kpath_{tag}_vecs"])
+        assert mags.dtype == vecs.dtype == np.float32
+    mags, vecs = kspace.k_path(lat, "x", 1.0, 9, lat_param=5.431)
+    np.testing.assert_array_equal(mags, g["kpath_lat_mags"])
+    np.testing.assert_array_equal(vecs, g["kpath_lat_vecs"])
+    mags, vecs = kspace.k_path(lat, [0, 1, 0], 2.0, 1)
+    np.testing.assert_array_equal(mags, g["kpath_nk1_mags"])
+    np.testing.assert_array_equal(vecs, g["kpath_nk1_vecs"])
+    with pytest.raises(ValueError):
+        kspace.k_path(lat, "x", 1.0, 0)
+
+
+def test_kgrid_matches_reference(gold_si):
+    for plane in ("xy", "yz", "zx"):
+        empty, vecs, shape = kspace.k_grid(plane, (-1.5, 2.0), (-0.5, 1.0), 4, 3, 0.25)
+        assert empty.size == 0 and empty.dtype == np.float32
+        np.testing.assert_array_equal(vecs, gold_si[f"kgrid_{plane}_vecs"])
+        assert shape == tuple(gold_si[f"kgrid_{plane}_shape"])
+    with pytest.raises(ValueError):
+        kspace.k_grid("xx", (0, 1), (0, 1), 2, 2)
+    with pytest.raises(ValueError):
+        kspace.k_grid("xy", (0, 1), (0, 1), 0, 2)
+
+
+def test_graphene_lattice(gold_gr):
+    lat = kspace.Lattice.from_box(gold_gr["box_matrix"], *gold_gr["cells"])
+    np.testing.assert_array_equal(lat.recip_vecs_prim, gold_gr["recip_vecs_prim"])
+    mags, vecs = kspace.k_path(lat, [1, 0, 0], 4.0, 10)
+    np.testing.assert_array_equal(vecs, gold_gr["kpath_vecs"])
+
+
+def test_lattice_errors():
+    box = np.eye(3, dtype=np.float32) * 10
+    with pytest.raises(ValueError):
+        kspace.Lattice.from_box(box, 0, 1, 1)
+    flat = box.copy(); flat[2] = 0
+    with pytest.raises(ValueError):
+        kspace.Lattice.from_box(flat, 1, 1, 1)
+
+
+# ---- group rules
+TYPES = np.array([1, 2, 1, 2, 1, 3], np.int32)
+
+
+def test_groups_types_flat():
+    coh = G.resolve_sed_groups(TYPES, 6, basis_atom_types=[1, 2], summation_mode="coherent")
+    assert len(coh) == 1 and list(coh[0]) == [0, 1, 2, 3, 4]
+    inc = G.resolve_sed_groups(TYPES, 6, basis_atom_types=[1, 2], summation_mode="incoherent")
+    assert [list(x) for x in inc] == [[0, 2, 4], [1, 3]]
+    cplx, proj = G.plan_sed_groups(inc, "incoherent")
+    assert not cplx and len(proj) == 2
+
+
+def test_groups_single_group_incoherent_is_complex():
+    one = G.resolve_sed_groups(TYPES, 6, basis_atom_types=[1], summation_mode="incoherent")
+    cplx, proj = G.plan_sed_groups(one, "incoherent")
+    assert cplx and list(proj[0]) == [0, 2, 4]
+    nested = G.resolve_sed_groups(TYPES, 6, basis_atom_types=[[1, 2]], summation_mode="incoherent")
+    assert G.plan_sed_groups(nested, "incoherent")[0]
+
+
+def test_groups_unknown_type_falls_back_to_all():
+    out = G.resolve_sed_groups(TYPES, 6, basis_atom_types=[7], summation_mode="incoherent")
+    assert len(out) == 1 and list(out[0]) == list(range(6))
+
+
+def test_groups_indices_and_errors():
+    out = G.resolve_sed_groups(TYPES, 6, basis_atom_indices=[[0, 1], [2, 3]], summation_mode="incoherent")
+    assert [list(x) for x in out] == [[0, 1], [2, 3]]
+    cplx, proj = G.plan_sed_groups(G.resolve_sed_groups(TYPES, 6, basis_atom_indices=[[0, 1], [1, 3]]), "coherent")
+    assert cplx and list(proj[0]) == [0, 1, 3]
+    dup = G.resolve_sed_groups(TYPES, 6, basis_atom_indices=[3, 1, 1])
+    assert list(dup[0]) == [3, 1, 1]                      # a single flat list keeps order and duplicates
+    with pytest.raises(ValueError):
+        G.resolve_sed_groups(TYPES, 6, basis_atom_indices=[0, 6])
+    with pytest.raises(ValueError):
+        G.resolve_sed_groups(TYPES, 6, basis_atom_types=[1, [2]])
+    both = G.resolve_sed_groups(TYPES, 6, basis_atom_indices=[0], basis_atom_types=[2])
+    assert list(both[0]) == [1, 3]                        # types win
+
+
+def test_ised_groups_flat_types_are_per_type():
+    out = G.resolve_ised_groups(TYPES, 6, basis_atom_types_ised=[1, 2])
+    assert [list(x) for x in out] == [[0, 2, 4], [1, 3]]
+    assert len(G.resolve_ised_groups(TYPES, 6)) == 1
+    assert G.resolve_ised_groups(TYPES, 6, basis_atom_types_ised=[9]) == []
+    with pytest.raises(ValueError):
+        G.resolve_ised_groups(TYPES, 6, basis_atom_idx_ised=[0, 99])
+
+
+# ---- SED container (reference tests/test_sed.py)
+@pytest.fixture
+def sed_data():
+    rng = np.random.default_rng(3)
+    s = (rng.random((10, 5, 3)) + 1j * rng.random((10, 5, 3))).astype(np.complex64)
+    return dict(sed=s, freqs=np.linspace(0, 10, 10, dtype=np.float32),
+                k_points=np.linspace(0, 1, 5, dtype=np.float32),
+                k_vectors=rng.random((5, 3)).astype(np.float32),
+                phase=rng.random((10, 5)).astype(np.float32))
+
+
+def test_sed_intensity_and_dict_access(sed_data):
+    obj = SED(**sed_data)
+    expected = np.sum(np.abs(sed_data["sed"]) ** 2, axis=-1).astype(np.float32)
+    np.testing.assert_array_equal(obj.intensity, expected)
+    assert obj["sed"] is obj.sed and "phase" in obj and set(obj.keys()) >= {"sed", "freqs", "is_complex"}
+    np.testing.assert_array_equal(obj["intensity"], expected)
+    with pytest.raises(KeyError):
+        obj["nope"]
+    empty = SED(sed=np.array([]).reshape(0, 0, 3), freqs=np.array([]), k_points=np.array([]),
+                k_vectors=np.array([]).reshape(0, 3))
+    assert empty.intensity.shape == (0, 0)
+
+
+def test_sed_save_load(sed_data, tmp_path):
+    obj = SED(**sed_data, k_grid_shape=(5, 1))
+    obj.save(tmp_path / "run1")
+    for suffix in (".sed.npy", ".freqs.npy", ".k_points.npy", ".k_vectors.npy", ".phase.npy", ".k_grid_shape.npy"):
+        assert (tmp_path / "run1").with_suffix(suffix).exists()
+    back = SED.load(tmp_path / "run1")
+    np.testing.assert_array_equal(back.sed, obj.sed)
+    np.testing.assert_array_equal(back.phase, obj.phase)
+    assert back.k_grid_shape == (5, 1)
+    with pytest.raises(FileNotFoundError):
+        SED.load(tmp_path / "missing")
+
+
+def test_trajectory_validation():
+    ok = dict(positions=np.zeros((4, 3, 3), np.float32), velocities=np.zeros((4, 3, 3), np.float32),
+              types=np.ones(3, np.int32), timesteps=np.arange(4), box_matrix=np.eye(3, dtype=np.float32),
+              box_lengths=np.ones(3, np.float32), box_tilts=np.zeros(3, np.float32), dt_ps=0.001)
+    t = Trajectory(**ok)
+    assert t.n_frames == 4 and t.n_atoms == 3
+    for key, bad in (("positions", np.zeros((4, 3, 2))), ("velocities", np.zeros((5, 3, 3))),
+                     ("types", np.ones((3, 1))), ("timesteps", np.arange(5)),
+                     ("box_matrix", np.eye(2)), ("box_lengths", np.ones(2)), ("box_tilts", np.ones(4))):
+        with pytest.raises(ValueError):
+            Trajectory(**{**ok, key: bad})

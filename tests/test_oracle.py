@@ -1,0 +1,141 @@
+"""The oracle must reproduce the REAL reference's outputs (tests/golden, made by
+oracle/make_golden.py) - bit for bit on the float32 path when NumPy/OpenBLAS match
+the recorded environment, and to rounding otherwise."""
+import numpy as np
+import pytest
+
+from oracle import psa_oracle as O
+
+
+def _same_env(gold) -> bool:
+    return np.__version__.split(".")[:2] == eval(str(gold["_env"]))["numpy"].split(".")[:2]
+
+
+def _check(new, ref, exact):
+    assert new.shape == ref.shape and new.dtype == ref.dtype
+    if exact:
+        np.testing.assert_array_equal(new, ref)
+    else:
+        scale = np.abs(ref).max()
+        np.testing.assert_allclose(new, ref, rtol=0, atol=2e-6 * scale)
+
+
+SED_CASES = {
+    "coh_all_100": ("kpath_100_vecs", {}),
+    "coh_all_110": ("kpath_110_vecs", {}),
+    "coh_all_111": ("kpath_111_vecs", {}),
+    "coh_all_100_chunk5": ("kpath_100_vecs", dict(k_chunk_size=5)),
+    "coh_types12": ("kpath_110_vecs", dict(basis_atom_types=[1, 2], summation_mode="coherent")),
+    "inc_types12": ("kpath_110_vecs", dict(basis_atom_types=[1, 2], summation_mode="incoherent")),
+    "inc_types1": ("kpath_110_vecs", dict(basis_atom_types=[1], summation_mode="incoherent")),
+    "inc_types_nested": ("kpath_110_vecs", dict(basis_atom_types=[[1, 2]], summation_mode="incoherent")),
+    "inc_types_unknown": ("kpath_100_vecs", dict(basis_atom_types=[7], summation_mode="incoherent")),
+    "inc_types_1_and_unknown": ("kpath_100_vecs", dict(basis_atom_types=[1, 7], summation_mode="incoherent")),
+    "inc_indices": ("kpath_100_vecs", dict(basis_atom_indices=[[0, 1, 5, 9], [2, 3, 40]],
+                                           summation_mode="incoherent")),
+    "coh_indices_union": ("kpath_100_vecs", dict(basis_atom_indices=[[0, 1, 5, 9], [2, 3, 5]],
+                                                 summation_mode="coherent")),
+    "coh_indices_flat_dup": ("kpath_100_vecs", dict(basis_atom_indices=[3, 1, 1, 20])),
+    "coh_indices_ndarray": ("kpath_100_vecs", dict(basis_atom_indices=np.array([4, 8, 15, 16, 23, 42]))),
+    "inc_all": ("kpath_100_vecs", dict(summation_mode="incoherent")),
+    "kgrid_xy": ("kgrid_xy_vecs", {}),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SED_CASES))
+def test_calculate_matches_reference(gold_si, name):
+    kkey, kw = SED_CASES[name]
+    g = gold_si
+    res = O.calculate(g["positions"], g["velocities"], g["types"], float(g["dt_ps"]), g[kkey], **kw)
+    assert res["is_complex"] == bool(g[f"cplx_{name}"])
+    _check(res["sed"], g[f"sed_{name}"], _same_env(g))
+    np.testing.assert_array_equal(res["freqs"], g["freqs"])
+
+
+def test_displacement_mode(gold_si):
+    g = gold_si
+    res = O.calculate(g["positions"], g["velocities"], g["types"], float(g["dt_ps"]),
+                      g["kpath_100_vecs"], use_displacements=True)
+    _check(res["sed"], g["sed_disp_coh_all_100"], _same_env(g))
+    res = O.calculate(g["positions"], g["velocities"], g["types"], float(g["dt_ps"]),
+                      g["kpath_110_vecs"], basis_atom_types=[1, 2], summation_mode="incoherent",
+                      use_displacements=True)
+    _check(res["sed"], g["sed_disp_inc_types12"], _same_env(g))
+
+
+def test_odd_frame_count(gold_si):
+    g = gold_si
+    res = O.calculate(g["positions"][:250], g["velocities"][:250], g["types"], float(g["dt_ps"]),
+                      g["kpath_100_vecs"])
+    _check(res["sed"], g["sed_odd250_coh_all_100"], _same_env(g))
+
+
+def test_intensity(gold_si):
+    np.testing.assert_array_equal(O.intensity(gold_si["sed_coh_all_100"]), gold_si["intensity_coh_all_100"])
+
+
+def test_fp64_oracle_is_close_to_reference(gold_si):
+    g = gold_si
+    r64 = O.calculate_fp64(g["positions"], g["velocities"], g["types"], float(g["dt_ps"]), g["kpath_110_vecs"])
+    ref = g["sed_coh_all_110"]
+    assert r64["sed"].dtype == np.complex128
+    assert np.abs(r64["sed"] - ref).max() < 5e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("axis,pair", [("x", (1, 2)), ("y", (0, 2)), ("z", (0, 1))])
+def test_chiral_phase_c(gold_gr, axis, pair):
+    s = gold_gr["sed_coh"]
+    ph = O.chiral_phase(s[:, :, pair[0]], s[:, :, pair[1]], "C")
+    _check(ph, gold_gr[f"phase_C_{axis}"], _same_env(gold_gr))
+    assert np.abs(ph).max() <= np.pi / 2 + 1e-6
+
+
+@pytest.mark.parametrize("opt", ["A", "B"])
+def test_chiral_phase_ab(gold_gr, opt):
+    s = gold_gr["sed_coh"]
+    ph = O.chiral_phase(s[:, :, 0], s[:, :, 1], opt)
+    np.testing.assert_allclose(ph, gold_gr[f"phase_{opt}_z"], atol=2e-3)   # acos/asin are ill-conditioned at +-1
+    assert np.median(np.abs(ph - gold_gr[f"phase_{opt}_z"])) < 1e-6
+
+
+def test_chiral_phase_shape_mismatch():
+    with pytest.raises(ValueError):
+        O.chiral_phase(np.zeros((2, 2), np.complex64), np.zeros((2, 3), np.complex64))
+    assert O.chiral_phase(np.zeros((0, 4), np.complex64), np.zeros((0, 4), np.complex64)).shape == (0, 4)
+
+
+def _ised_args(g):
+    k_hat = np.array([1, 0, 0], np.float32)
+    mags, vecs = O.k_path(None, None, k_hat, 1.0, 9, lat_param=5.431)
+    np.testing.assert_array_equal(mags, g["kpath_lat_mags"])
+    return k_hat, mags, vecs
+
+
+def test_ised_types_float(gold_si):
+    g = gold_si
+    k_hat, mags, vecs = _ised_args(g)
+    groups = [np.where(g["types"] == 1)[0], np.where(g["types"] == 2)[0]]
+    out = O.ised(g["positions"], g["velocities"], g["types"], float(g["dt_ps"]), k_hat, mags, vecs,
+                 float(g["ised_k_target"]), float(g["ised_w_target"]), groups, rescale_factor=0.5, n_frames=8)
+    _check(out["frames"], g["ised_types_float"], _same_env(g))
+
+
+def test_ised_auto(gold_si):
+    g = gold_si
+    k_hat, mags, vecs = _ised_args(g)
+    out = O.ised(g["positions"], g["velocities"], g["types"], float(g["dt_ps"]), k_hat, mags, vecs,
+                 float(g["ised_k_target"]), float(g["ised_w_target"]), [np.arange(len(g["types"]))],
+                 rescale_factor="auto", n_frames=8)
+    _check(out["frames"], g["ised_all_auto"], _same_env(g))
+    groups = [np.array([0, 1, 2, 3]), np.array([10, 11, 12])]
+    out = O.ised(g["positions"], g["velocities"], g["types"], float(g["dt_ps"]), k_hat, mags, vecs,
+                 0.3, float(g["ised_w_target"]) * 0.5, groups, rescale_factor="auto", n_frames=8)
+    _check(out["frames"], g["ised_idx_auto"], _same_env(g))
+
+
+def test_parity_report_shape():
+    rng = np.random.default_rng(0)
+    i_ref = rng.random((16, 5)).astype(np.float32)
+    rep = O.parity_report(i_ref * (1 + 1e-7), i_ref, i_ref.astype(np.float64))
+    assert rep["global_peak_equal"] and rep["per_k_peak_equal"]
+    assert rep[1e-6]["new_ref"]["max"] < 1e-6
