@@ -1,0 +1,136 @@
+// extern "C" surface of libpsa_b200.so (declared in include/psa_b200.h): argument validation,
+// error plumbing, and dispatch to the kernel launchers.  No state is kept between calls.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace psa {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t err, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)err, cudaGetErrorString(err), what);
+  return PSA_ERR_CUDA;
+}
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace psa
+
+using namespace psa;
+
+extern "C" {
+
+int psa_version(void) { return 100; }   // 0.1.0
+
+const char* psa_last_error(void) { return g_error; }
+
+int psa_device_check(int device) {
+  cudaDeviceProp prop;
+  PSA_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+    return PSA_ERR_UNSUPPORTED;
+  }
+  return PSA_OK;
+}
+
+int64_t psa_pitch(int64_t n_sel) { return round_up(n_sel > 0 ? n_sel : 1, 64); }
+
+int psa_mean_positions(const float* pos, int64_t n_t, int64_t n_a, float* mean, void* stream) {
+  PSA_REQUIRE(n_t >= 0 && n_a >= 0, "psa_mean_positions: negative extent");
+  PSA_REQUIRE(n_t == 0 || n_a == 0 || (pos && mean), "psa_mean_positions: null pointer");
+  PSA_REQUIRE(n_t > 0 || n_a == 0, "psa_mean_positions: zero frames");
+  return launch_mean_positions(pos, n_t, n_a, mean, as_stream(stream));
+}
+
+int psa_digitize(const float* data, const float* mean, const int32_t* idx, int64_t n_t, int64_t n_a,
+                 int64_t n_sel, int64_t pitch, int8_t* dig, int32_t* expo, void* stream) {
+  PSA_REQUIRE(data && dig && expo, "psa_digitize: null pointer");
+  PSA_REQUIRE(n_t > 0 && n_a > 0 && n_sel > 0, "psa_digitize: empty input (n_t=%lld n_a=%lld n_sel=%lld)",
+              (long long)n_t, (long long)n_a, (long long)n_sel);
+  PSA_REQUIRE(idx != nullptr || n_sel == n_a, "psa_digitize: n_sel must equal n_a when idx is NULL");
+  PSA_REQUIRE(pitch >= n_sel && pitch % 64 == 0, "psa_digitize: pitch must be a multiple of 64 and >= n_sel");
+  return launch_digitize(data, mean, idx, n_t, n_a, n_sel, pitch, dig, expo, as_stream(stream));
+}
+
+int psa_phase_digits(const float* kvecs, int64_t n_k, const float* mean, const int32_t* idx, int64_t n_sel,
+                     int64_t pitch, int64_t rows_alloc, int8_t* adig, void* stream) {
+  PSA_REQUIRE(kvecs && mean && adig, "psa_phase_digits: null pointer");
+  PSA_REQUIRE(n_k > 0 && n_k <= 65535, "psa_phase_digits: n_k per call must be in [1, 65535] (chunk the k list)");
+  PSA_REQUIRE(n_sel > 0 && pitch >= n_sel && pitch % 64 == 0, "psa_phase_digits: bad n_sel/pitch");
+  PSA_REQUIRE(rows_alloc >= 2 * n_k, "psa_phase_digits: rows_alloc < 2 n_k");
+  return launch_phase_digits(kvecs, n_k, mean, idx, n_sel, pitch, rows_alloc, adig, as_stream(stream));
+}
+
+int psa_project(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig, const int32_t* expo,
+                int64_t n_t, int64_t n_sel, int64_t pitch, float* P, int64_t ldp, int impl, void* stream) {
+  PSA_REQUIRE(adig && bdig && expo && P, "psa_project: null pointer");
+  PSA_REQUIRE(rows > 0 && rows <= rows_alloc && n_t > 0 && n_sel > 0, "psa_project: bad extents");
+  PSA_REQUIRE(pitch >= n_sel && pitch % 64 == 0, "psa_project: pitch must be a multiple of 64 and >= n_sel");
+  PSA_REQUIRE(ldp >= n_t && ldp % 4 == 0, "psa_project: ldp must be a multiple of 4 and >= n_t");
+  PSA_REQUIRE(((uintptr_t)adig % 16) == 0 && ((uintptr_t)bdig % 16) == 0 && ((uintptr_t)P % 16) == 0,
+              "psa_project: buffers must be 16-byte aligned");
+  if (impl == PSA_PROJECT_TENSOR)
+    return launch_project_tc(adig, rows, rows_alloc, bdig, expo, n_t, n_sel, pitch, P, ldp, as_stream(stream));
+  if (impl == PSA_PROJECT_SIMT)
+    return launch_project_simt(adig, rows, rows_alloc, bdig, expo, n_t, n_sel, pitch, P, ldp, as_stream(stream));
+  set_error("psa_project: unknown impl %d", impl);
+  return PSA_ERR_BAD_ARG;
+}
+
+int psa_twiddles(int64_t n, float* tw, void* stream) {
+  PSA_REQUIRE(n > 0 && tw, "psa_twiddles: bad arguments");
+  return launch_twiddles(n, reinterpret_cast<float2*>(tw), as_stream(stream));
+}
+
+int psa_fft_sed(const float* P, int64_t n_groups, int64_t group_stride, int64_t n_k, int64_t n_t, int64_t ldp,
+                const float* tw, int mode, void* out, int64_t n_k_total, int64_t k_offset, void* stream) {
+  PSA_REQUIRE(P && tw && out, "psa_fft_sed: null pointer");
+  PSA_REQUIRE(n_groups >= 1 && n_k > 0 && n_t > 0 && ldp >= n_t, "psa_fft_sed: bad extents");
+  PSA_REQUIRE(k_offset >= 0 && k_offset + n_k <= n_k_total, "psa_fft_sed: k range outside the result");
+  PSA_REQUIRE(mode == PSA_MODE_INCOHERENT || n_groups == 1, "psa_fft_sed: coherent mode takes one group");
+  return launch_fft(P, n_groups, group_stride, n_k, n_t, ldp, reinterpret_cast<const float2*>(tw), mode, out,
+                    n_k_total, k_offset, as_stream(stream));
+}
+
+int psa_chiral_phase(const float* z1, const float* z2, int64_t n, int64_t stride1, int64_t stride2, int opt,
+                     float* out, void* stream) {
+  PSA_REQUIRE(n >= 0 && (n == 0 || (z1 && z2 && out)), "psa_chiral_phase: bad arguments");
+  return launch_chiral(reinterpret_cast<const float2*>(z1), reinterpret_cast<const float2*>(z2), n, stride1, stride2,
+                       opt, out, as_stream(stream));
+}
+
+int psa_intensity(const float* sed, int64_t n_rows, int n_pol, float* out, void* stream) {
+  PSA_REQUIRE(n_rows >= 0 && n_pol > 0 && (n_rows == 0 || (sed && out)), "psa_intensity: bad arguments");
+  return launch_intensity(reinterpret_cast<const float2*>(sed), n_rows, n_pol, out, as_stream(stream));
+}
+
+int psa_ised_frames(const float* mean, const double* amp, const float* khat, float k_act, double scale, int add_mean,
+                    int64_t n_a, int64_t n_frames, float* out, void* stream) {
+  PSA_REQUIRE(n_a >= 0 && n_frames >= 0, "psa_ised_frames: negative extent");
+  PSA_REQUIRE(n_a * n_frames == 0 || (mean && amp && khat && out), "psa_ised_frames: null pointer");
+  return launch_ised(mean, amp, khat, k_act, scale, add_mean, n_a, n_frames, out, as_stream(stream));
+}
+
+int psa_disp_moments(const float* pos, const float* mean, const int32_t* idx, int64_t n_t, int64_t n_a,
+                     int64_t n_sel, double* out2, void* stream) {
+  PSA_REQUIRE(pos && mean && out2, "psa_disp_moments: null pointer");
+  PSA_REQUIRE(idx != nullptr || n_sel == n_a, "psa_disp_moments: n_sel must equal n_a when idx is NULL");
+  return launch_disp_moments(pos, mean, idx, n_t, n_a, n_sel, out2, as_stream(stream));
+}
+
+int psa_absmax(const float* x, int64_t n, float* out, void* stream) {
+  PSA_REQUIRE(out && (n == 0 || x), "psa_absmax: null pointer");
+  return launch_absmax(x, n, out, as_stream(stream));
+}
+
+}  // extern "C"

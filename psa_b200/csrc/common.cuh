@@ -1,0 +1,87 @@
+// Shared declarations of the psa_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/psa_b200.h"
+
+namespace psa {
+
+// ---- error plumbing: every entry point returns a status, the text is thread-local
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t err, const char* what);
+
+#define PSA_CUDA(call)                                            \
+  do {                                                            \
+    cudaError_t _e = (call);                                      \
+    if (_e != cudaSuccess) return ::psa::cuda_fail(_e, #call);    \
+  } while (0)
+
+#define PSA_REQUIRE(cond, ...)                                    \
+  do {                                                            \
+    if (!(cond)) {                                                \
+      ::psa::set_error(__VA_ARGS__);                              \
+      return PSA_ERR_BAD_ARG;                                     \
+    }                                                             \
+  } while (0)
+
+inline int launch_status(const char* kernel) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, kernel);
+  return PSA_OK;
+}
+
+// ---- digit format shared by the digitiser, the phase generator and both projection kernels
+//
+// A real number x with |x| <= 1 (phase table) or |x| < 2^e (trajectory row) is held as the
+// integer X = rint(x * 2^(30-e)), |X| <= 2^30, written in balanced base 256:
+//     X = d0 + 256 d1 + 256^2 d2 + 256^3 d3,   d0..d2 in [-128,127], d3 in [-64,64].
+// Each digit plane is an int8 matrix the tensor cores multiply exactly (int32 accumulate).
+constexpr int kSlices = 4;
+constexpr int kFracBits = 30;
+// digit-pair classes kept by the projection: i + j >= 3  (10 products, weights 256^(i+j))
+constexpr int kMinClass = 3;
+constexpr int kClasses = 4;
+
+__host__ __device__ inline void balanced_digits(int32_t x, int8_t d[4]) {
+  int32_t r = x;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    int8_t lo = (int8_t)(r & 0xFF);
+    d[i] = lo;
+    r = (r - (int32_t)lo) >> 8;   // exact: r - lo is a multiple of 256
+  }
+  d[3] = (int8_t)r;
+}
+
+constexpr int kExpMin = -80;   // exponent stored for an all-zero row
+constexpr int kExpMax = 100;
+
+inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// device-side kernels' host launchers (one per .cu file)
+int launch_mean_positions(const float* pos, int64_t n_t, int64_t n_a, float* mean, cudaStream_t s);
+int launch_digitize(const float* data, const float* mean, const int32_t* idx, int64_t n_t, int64_t n_a,
+                    int64_t n_sel, int64_t pitch, int8_t* dig, int32_t* expo, cudaStream_t s);
+int launch_phase_digits(const float* kvecs, int64_t n_k, const float* mean, const int32_t* idx,
+                        int64_t n_sel, int64_t pitch, int64_t rows_alloc, int8_t* adig, cudaStream_t s);
+int launch_project_tc(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig,
+                      const int32_t* expo, int64_t n_t, int64_t n_sel, int64_t pitch, float* P,
+                      int64_t ldp, cudaStream_t s);
+int launch_project_simt(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig,
+                        const int32_t* expo, int64_t n_t, int64_t n_sel, int64_t pitch, float* P,
+                        int64_t ldp, cudaStream_t s);
+int launch_twiddles(int64_t n, float2* tw, cudaStream_t s);
+int launch_fft(const float* P, int64_t n_groups, int64_t group_stride, int64_t n_k, int64_t n_t, int64_t ldp,
+               const float2* tw, int mode, void* out, int64_t n_k_total, int64_t k_offset, cudaStream_t s);
+int launch_chiral(const float2* z1, const float2* z2, int64_t n, int64_t stride1, int64_t stride2,
+                  int opt, float* out, cudaStream_t s);
+int launch_intensity(const float2* sed, int64_t n_rows, int n_pol, float* out, cudaStream_t s);
+int launch_ised(const float* mean, const double* amp, const float* khat, float k_act, double scale, int add_mean,
+                int64_t n_a, int64_t n_frames, float* out, cudaStream_t s);
+int launch_disp_moments(const float* pos, const float* mean, const int32_t* idx, int64_t n_t, int64_t n_a,
+                        int64_t n_sel, double* out2, cudaStream_t s);
+int launch_absmax(const float* x, int64_t n, float* out, cudaStream_t s);
+
+}  // namespace psa

@@ -1,0 +1,339 @@
+// Projection on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+//   P[row][pol][t] = sum_atoms phase[row][atom] * data[t][atom][pol]
+//
+// Both operands arrive as four int8 digit planes (balanced base 256, see common.cuh), so the
+// float32-grade contraction becomes ten exact s8 x s8 -> s32 tensor-core products per K step:
+// every digit pair (i, j) with i + j >= 3, accumulated per class i + j in its own TMEM columns.
+// The epilogue recombines the four int32 class sums in int64 and rounds ONCE to float32, so the
+// result does not depend on tile shapes, K order or clock - it is reproducible bit for bit by
+// the integer model in tests/.
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0 lane 0 : TMA producer  - 2 bulk tensor copies per stage (A: 4x128x64 B, B: 4x128x64 B),
+//                   64-byte swizzle, 3-stage mbarrier ring
+//   warp 1 lane 0 : MMA issuer    - 20 tcgen05.mma.kind::i8 (M128 N128 K32) per stage into
+//                   4 x 128 TMEM columns, tcgen05.commit releases the stage / publishes the tile
+//   warps 2..5    : epilogue      - tcgen05.ld 32x32b, int64 recombination, float32 store
+// TMEM is fully used by the four accumulator classes (4 x 128 columns), so the epilogue of a tile
+// is not overlapped with the next tile's MMAs; with >= 2048 atoms it is < 10 % of the tile time.
+#include <cuda.h>
+
+#include "project_common.cuh"
+
+namespace psa {
+namespace tc {
+
+constexpr int BM = 128;            // rows (2 per k-point) per tile == TMEM lanes
+constexpr int BN = 128;            // frames per tile == TMEM columns per class
+constexpr int BK = 64;             // atoms per stage == one 64-byte swizzle row
+constexpr int UMMA_K = 32;         // atoms per tcgen05.mma.kind::i8
+constexpr int STAGES = 3;
+constexpr int SLICE_BYTES = 128 * BK;                  // one digit plane of a tile
+constexpr int OPERAND_BYTES = kSlices * SLICE_BYTES;   // 32 KiB
+constexpr int STAGE_BYTES = 2 * OPERAND_BYTES;         // 64 KiB
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
+constexpr int THREADS = 192;
+constexpr uint32_t TMEM_COLS = 512;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+#define PSA_TMEM_LD16(r, addr)                                                                         \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),   \
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) \
+               : "r"(addr))
+
+// Shared-memory matrix descriptor, K-major operand, 64-byte swizzle: rows of 64 B, 8-row groups
+// 512 B apart (SBO), descriptor version 1 (sm_100), layout type 4 = SWIZZLE_64B.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+// Instruction descriptor: D = s32, A = B = s8, both K-major, M = 128, N = 128.
+constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct TileCoord {
+  int m_tile, pol, t_tile;
+};
+__device__ __forceinline__ TileCoord decode_tile(int tile, int m_tiles, int n_tiles) {
+  TileCoord c;
+  c.m_tile = tile % m_tiles;          // row tiles fastest: concurrent CTAs share the same B strip
+  int n = tile / m_tiles;
+  c.pol = n / n_tiles;
+  c.t_tile = n % n_tiles;
+  return c;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const int32_t* __restrict__ expo, float* __restrict__ P, int rows, int n_t, int64_t ldp,
+                  int a_begin, int a_end, int accumulate, int m_tiles, int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_b) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int total_tiles = m_tiles * n_tiles * 3;
+  const int num_kb = (a_end - a_begin + BK - 1) / BK;
+
+  if (warp == 0) {
+    if (lane == 0) {                                           // ---------------- TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        TileCoord tc = decode_tile(tile, m_tiles, n_tiles);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          uint32_t dst = smem_u32(smem + stage * STAGE_BYTES);
+          int atom0 = a_begin + kb * BK;
+          tma_load_3d(dst, &tmap_a, &full_bar[stage], atom0, tc.m_tile * BM, 0);
+          tma_load_3d(dst + OPERAND_BYTES, &tmap_b, &full_bar[stage], atom0, tc.t_tile * BN, tc.pol * kSlices);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                           // ---------------- MMA issuer
+      int stage = 0;
+      uint32_t phase = 0, tile_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tmem_empty, tile_phase ^ 1);                 // epilogue has drained the accumulators
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_base = a_base + OPERAND_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+#pragma unroll
+            for (int si = 0; si < kSlices; ++si) {
+#pragma unroll
+              for (int sj = 0; sj < kSlices; ++sj) {
+                if (si + sj < kMinClass) continue;
+                const uint64_t da = smem_desc(a_base + si * SLICE_BYTES + ks * UMMA_K);
+                const uint64_t db = smem_desc(b_base + sj * SLICE_BYTES + ks * UMMA_K);
+                const uint32_t d = tmem_base + (uint32_t)((si + sj - kMinClass) * BN);
+                // the first product issued into each class (sj == 3) overwrites, the rest accumulate
+                const uint32_t acc = (kb > 0 || ks > 0 || sj != kSlices - 1) ? 1u : 0u;
+                tc_mma_i8(d, da, db, kIdesc, acc);
+              }
+            }
+          }
+          tc_commit(&empty_bar[stage]);                        // stage reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tmem_full);                                  // accumulators complete
+        tile_phase ^= 1;
+      }
+    }
+  } else {                                                     // ---------------- epilogue warps 2..5
+    const int quarter = warp & 3;                              // TMEM lane quarter this warp may read
+    uint32_t tile_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      TileCoord tc = decode_tile(tile, m_tiles, n_tiles);
+      mbar_wait(tmem_full, tile_phase);
+      tc_fence_after();
+      const int row = tc.m_tile * BM + quarter * 32 + lane;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      float* prow = P + ((int64_t)row * 3 + tc.pol) * ldp;
+      const int32_t* erow = expo + (int64_t)tc.pol * n_t;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r0[16], r1[16], r2[16], r3[16];
+        PSA_TMEM_LD16(r0, lane_addr + 0 * BN + c0);
+        PSA_TMEM_LD16(r1, lane_addr + 1 * BN + c0);
+        PSA_TMEM_LD16(r2, lane_addr + 2 * BN + c0);
+        PSA_TMEM_LD16(r3, lane_addr + 3 * BN + c0);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int t0 = tc.t_tile * BN + c0;
+        if (row < rows) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const int t = t0 + v * 4;
+            if (t >= ldp) break;
+            float4 o;
+            float* of = reinterpret_cast<float*>(&o);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int tt = t + u;
+              const int e = tt < n_t ? __ldg(erow + tt) : kExpMin;
+              const int i = v * 4 + u;
+              of[u] = combine_classes((int32_t)r0[i], (int32_t)r1[i], (int32_t)r2[i], (int32_t)r3[i], e);
+            }
+            float4* dst = reinterpret_cast<float4*>(prow + t);
+            if (accumulate) {
+              float4 old = *dst;
+              o.x = __fadd_rn(old.x, o.x); o.y = __fadd_rn(old.y, o.y);
+              o.z = __fadd_rn(old.z, o.z); o.w = __fadd_rn(old.w, o.w);
+            }
+            *dst = o;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty);
+      tile_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// 3-D map over int8 digit planes [outer][mid][n_sel], row pitch `pitch` bytes, box 64 x 128 x 4.
+static int make_map(CUtensorMap* map, const int8_t* base, int64_t n_sel, int64_t pitch, int64_t mid, int64_t mid_alloc,
+                    int64_t outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return PSA_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)n_sel, (cuuint64_t)mid, (cuuint64_t)outer};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)(mid_alloc * pitch)};
+  cuuint32_t box[3] = {BK, 128, kSlices};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (n_sel=%lld pitch=%lld mid=%lld outer=%lld)", (int)r,
+              (long long)n_sel, (long long)pitch, (long long)mid, (long long)outer);
+    return PSA_ERR_CUDA;
+  }
+  return PSA_OK;
+}
+
+}  // namespace tc
+
+int launch_project_tc(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig,
+                      const int32_t* expo, int64_t n_t, int64_t n_sel, int64_t pitch, float* P, int64_t ldp,
+                      cudaStream_t s) {
+  using namespace tc;
+  if (rows == 0 || n_t == 0) return PSA_OK;
+  PSA_REQUIRE(n_sel > 0, "psa_project: empty atom selection");
+  PSA_REQUIRE(rows < (1 << 30) && n_t < (1 << 30) && n_sel < (1 << 30), "psa_project: extent too large");
+  CUtensorMap map_a, map_b;
+  int st = make_map(&map_a, adig, n_sel, pitch, rows, rows_alloc, kSlices);
+  if (st != PSA_OK) return st;
+  st = make_map(&map_b, bdig, n_sel, pitch, n_t, n_t, 3 * kSlices);
+  if (st != PSA_OK) return st;
+
+  static bool attr_set = false;   // per-process, idempotent
+  if (!attr_set) {
+    PSA_CUDA(cudaFuncSetAttribute(project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  int dev = 0, sms = 0;
+  PSA_CUDA(cudaGetDevice(&dev));
+  PSA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int m_tiles = (int)((rows + BM - 1) / BM);
+  const int n_tiles = (int)((n_t + BN - 1) / BN);
+  const int total = m_tiles * n_tiles * 3;
+  const int grid = total < sms ? total : sms;
+
+  int pass = 0;
+  for (int64_t a0 = 0; a0 < n_sel; a0 += kMaxAtomsPerPass, ++pass) {
+    int64_t a1 = a0 + kMaxAtomsPerPass < n_sel ? a0 + kMaxAtomsPerPass : n_sel;
+    project_tc_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, expo, P, (int)rows, (int)n_t, ldp, (int)a0,
+                                                        (int)a1, pass > 0, m_tiles, n_tiles);
+    st = launch_status("project_tc_kernel");
+    if (st != PSA_OK) return st;
+  }
+  return PSA_OK;
+}
+
+}  // namespace psa

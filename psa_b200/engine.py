@@ -1,0 +1,248 @@
+"""Device-side orchestration of the SED hot path.
+
+PyTorch is used for exactly three things here: owning device buffers, streams,
+and host<->device copies.  Every arithmetic step is a call through the C ABI
+(``psa_b200._lib``) into hand-written sm_100a kernels; there is no tensor
+arithmetic in this file and no fallback if the library is missing.
+
+Pipeline for one ``calculate`` (reference: src/psa/core/sed_calculator.py:182-336)::
+
+    upload trajectory ─► mean positions ─► digit planes of the projected series   (once per group)
+    for each k-chunk:  phase digit planes ─► tensor-core projection ─► FFT + assembly into the result
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import threading
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+K_CHUNK_CAP = 1024            # k-points per chunk (2048 projection rows = 16 row tiles)
+_UPLOAD_CHUNK_BYTES = 256 << 20
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Engine:
+    """Thin, typed wrappers of the C entry points operating on torch CUDA tensors."""
+
+    def __init__(self, device: Optional[int] = None, project_impl: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("psa_b200 needs a CUDA device (B200, sm_100a); there is no CPU path.")
+        if device is None:
+            device = int(os.environ.get("PSA_B200_DEVICE", torch.cuda.current_device()))
+        self.device = torch.device("cuda", device)
+        _lib.check(_lib.load().psa_device_check(device))
+        if project_impl is None:
+            project_impl = int(os.environ.get("PSA_B200_PROJECT_IMPL", _lib.PROJECT_TENSOR))
+        self.project_impl = project_impl
+        self._twiddles: Dict[int, torch.Tensor] = {}
+        self.launches = 0          # kernels launched through this engine (bench reports it)
+
+    # -- helpers
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def empty(self, shape, dtype) -> torch.Tensor:
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    # -- kernels
+    def mean_positions(self, pos: torch.Tensor) -> torch.Tensor:
+        n_t, n_a, _ = pos.shape
+        mean = self.empty((n_a, 3), torch.float32)
+        _lib.call("psa_mean_positions", pos.data_ptr(), n_t, n_a, mean.data_ptr(), self.stream())
+        self.launches += 1
+        return mean
+
+    def digitize(self, data: torch.Tensor, mean: Optional[torch.Tensor], idx: Optional[torch.Tensor],
+                 n_sel: int) -> Tuple[torch.Tensor, torch.Tensor, int]:
+        n_t, n_a, _ = data.shape
+        pitch = int(_lib.load().psa_pitch(n_sel))
+        dig = self.empty((3, 4, n_t, pitch), torch.int8)
+        expo = self.empty((3, n_t), torch.int32)
+        _lib.call("psa_digitize", data.data_ptr(), _ptr(mean), _ptr(idx), n_t, n_a, n_sel, pitch,
+                  dig.data_ptr(), expo.data_ptr(), self.stream())
+        self.launches += 1
+        return dig, expo, pitch
+
+    def phase_digits(self, kvecs: torch.Tensor, mean: torch.Tensor, idx: Optional[torch.Tensor], n_sel: int,
+                     pitch: int, rows_alloc: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        n_k = kvecs.shape[0]
+        if out is None:
+            out = self.empty((4, rows_alloc, pitch), torch.int8)
+        _lib.call("psa_phase_digits", kvecs.data_ptr(), n_k, mean.data_ptr(), _ptr(idx), n_sel, pitch,
+                  rows_alloc, out.data_ptr(), self.stream())
+        self.launches += 1
+        return out
+
+    def project(self, adig: torch.Tensor, rows: int, rows_alloc: int, bdig: torch.Tensor, expo: torch.Tensor,
+                n_t: int, n_sel: int, pitch: int, P: torch.Tensor, ldp: int, impl: Optional[int] = None) -> None:
+        _lib.call("psa_project", adig.data_ptr(), rows, rows_alloc, bdig.data_ptr(), expo.data_ptr(), n_t, n_sel,
+                  pitch, P.data_ptr(), ldp, self.project_impl if impl is None else impl, self.stream())
+        self.launches += -(-n_sel // 32768)
+
+    def twiddles(self, n_t: int) -> torch.Tensor:
+        tw = self._twiddles.get(n_t)
+        if tw is None:
+            tw = self.empty((n_t, 2), torch.float32)
+            _lib.call("psa_twiddles", n_t, tw.data_ptr(), self.stream())
+            self.launches += 1
+            self._twiddles[n_t] = tw
+        return tw
+
+    def fft_sed(self, P: torch.Tensor, n_groups: int, group_stride: int, n_k: int, n_t: int, ldp: int,
+                mode: int, out: torch.Tensor, n_k_total: int, k_offset: int) -> None:
+        tw = self.twiddles(n_t)
+        _lib.call("psa_fft_sed", P.data_ptr(), n_groups, group_stride, n_k, n_t, ldp, tw.data_ptr(), mode,
+                  out.data_ptr(), n_k_total, k_offset, self.stream())
+        self.launches += 1
+
+    def chiral_phase(self, z1: torch.Tensor, z2: torch.Tensor, n: int, stride1: int, stride2: int, opt: str,
+                     out: torch.Tensor) -> None:
+        _lib.call("psa_chiral_phase", z1.data_ptr(), z2.data_ptr(), n, stride1, stride2, ord(opt),
+                  out.data_ptr(), self.stream())
+        self.launches += 1
+
+    def intensity(self, sed: torch.Tensor) -> torch.Tensor:
+        n_pol = sed.shape[-1]
+        n_rows = sed.numel() // n_pol
+        out = self.empty(sed.shape[:-1], torch.float32)
+        _lib.call("psa_intensity", sed.data_ptr(), n_rows, n_pol, out.data_ptr(), self.stream())
+        self.launches += 1
+        return out
+
+
+class DeviceTrajectory:
+    """A trajectory resident in HBM plus everything derived from it that is k-independent."""
+
+    def __init__(self, engine: Engine, positions: np.ndarray, velocities: np.ndarray):
+        self.engine = engine
+        self.n_t, self.n_a = positions.shape[0], positions.shape[1]
+        self._host = {"pos": positions, "vel": velocities}
+        self._dev: Dict[str, torch.Tensor] = {}
+        self._mean: Optional[torch.Tensor] = None
+        self._groups: Dict[Tuple, Tuple] = {}
+        self._lock = threading.RLock()
+        self.h2d_bytes = 0
+
+    # -- uploads (pinned source -> one async copy; pageable source -> chunked pinned staging)
+    def _upload(self, which: str) -> torch.Tensor:
+        dev = self._dev.get(which)
+        if dev is not None:
+            return dev
+        host = self._host[which]
+        if isinstance(host, torch.Tensor) and host.is_cuda:
+            dev = host.to(self.engine.device, torch.float32).contiguous()
+        else:
+            arr = host.numpy() if isinstance(host, torch.Tensor) else np.asarray(host)
+            if arr.dtype != np.float32 or not arr.flags.c_contiguous:
+                arr = np.ascontiguousarray(arr, dtype=np.float32)
+            src = torch.from_numpy(arr)
+            dev = torch.empty(src.shape, dtype=torch.float32, device=self.engine.device)
+            if src.is_pinned():
+                dev.copy_(src, non_blocking=True)
+            else:
+                flat_src, flat_dst = src.view(-1), dev.view(-1)
+                step = max(1, _UPLOAD_CHUNK_BYTES // 4)
+                bufs = [torch.empty(min(step, flat_src.numel()), dtype=torch.float32).pin_memory() for _ in range(2)]
+                events: List[Optional[torch.cuda.Event]] = [None, None]
+                for i, off in enumerate(range(0, flat_src.numel(), step)):
+                    n = min(step, flat_src.numel() - off)
+                    b = i & 1
+                    if events[b] is not None:
+                        events[b].synchronize()
+                    bufs[b][:n].copy_(flat_src[off:off + n])
+                    flat_dst[off:off + n].copy_(bufs[b][:n], non_blocking=True)
+                    events[b] = torch.cuda.Event()
+                    events[b].record(torch.cuda.current_stream(self.engine.device))
+            self.h2d_bytes += src.numel() * 4
+        self._dev[which] = dev
+        return dev
+
+    @property
+    def positions(self) -> torch.Tensor:
+        return self._upload("pos")
+
+    @property
+    def velocities(self) -> torch.Tensor:
+        return self._upload("vel")
+
+    def release(self, which: str) -> None:
+        self._dev.pop(which, None)
+
+    @property
+    def mean(self) -> torch.Tensor:
+        with self._lock:
+            if self._mean is None:
+                self._mean = self.engine.mean_positions(self.positions)
+            return self._mean
+
+    def group(self, idx: Optional[np.ndarray], use_displacements: bool) -> Tuple:
+        """``(idx_dev|None, n_sel, pitch, digits, exponents)`` for an atom selection (cached)."""
+        if idx is not None and idx.size == self.n_a and np.array_equal(idx, np.arange(self.n_a)):
+            idx = None
+        key = (use_displacements,
+               None if idx is None else hashlib.blake2b(np.ascontiguousarray(idx, np.int64).tobytes(),
+                                                         digest_size=16).hexdigest())
+        with self._lock:
+            hit = self._groups.get(key)
+            if hit is not None:
+                return hit
+            eng = self.engine
+            if idx is None:
+                idx_dev, n_sel = None, self.n_a
+            else:
+                idx_dev = torch.from_numpy(np.ascontiguousarray(idx, np.int32)).to(eng.device)
+                n_sel = int(idx.size)
+            if use_displacements:
+                dig, expo, pitch = eng.digitize(self.positions, self.mean, idx_dev, n_sel)
+            else:
+                dig, expo, pitch = eng.digitize(self.velocities, None, idx_dev, n_sel)
+            entry = (idx_dev, n_sel, pitch, dig, expo)
+            self._groups[key] = entry
+            return entry
+
+
+def sed_on_device(traj: DeviceTrajectory, k_vecs: np.ndarray, groups: Sequence[Optional[np.ndarray]],
+                  complex_out: bool, use_displacements: bool, k_chunk: int = K_CHUNK_CAP) -> torch.Tensor:
+    """Run the projection + FFT pipeline; returns the device-resident result.
+
+    ``groups``: atom index arrays (``None`` = all atoms).  ``complex_out`` -> complex64
+    ``(n_t, n_k, 3)`` from the single group; otherwise float32 ``(n_t, n_k)`` summed over groups.
+    """
+    eng = traj.engine
+    n_t, n_k = traj.n_t, int(k_vecs.shape[0])
+    if complex_out:
+        assert len(groups) == 1
+        out = torch.empty((n_t, n_k, 3), dtype=torch.complex64, device=eng.device)
+    else:
+        out = torch.empty((n_t, n_k), dtype=torch.float32, device=eng.device)
+    if n_k == 0:
+        return out
+    mean = traj.mean
+    entries = [traj.group(g, use_displacements) for g in groups]
+    kc = max(1, min(k_chunk, n_k, K_CHUNK_CAP))
+    rows_alloc = 2 * kc
+    ldp = (n_t + 3) // 4 * 4
+    kv_dev = torch.from_numpy(np.ascontiguousarray(k_vecs, np.float32)).to(eng.device)
+    P = eng.empty((len(entries), rows_alloc, 3, ldp), torch.float32)
+    group_stride = rows_alloc * 3 * ldp
+    adig_bufs: Dict[int, torch.Tensor] = {}
+    mode = _lib.MODE_COHERENT if complex_out else _lib.MODE_INCOHERENT
+    for k0 in range(0, n_k, kc):
+        nk = min(kc, n_k - k0)
+        for g, (idx_dev, n_sel, pitch, dig, expo) in enumerate(entries):
+            adig = adig_bufs.get(pitch)
+            if adig is None:
+                adig = adig_bufs[pitch] = eng.empty((4, rows_alloc, pitch), torch.int8)
+            eng.phase_digits(kv_dev[k0:k0 + nk], mean, idx_dev, n_sel, pitch, rows_alloc, out=adig)
+            eng.project(adig, 2 * nk, rows_alloc, dig, expo, n_t, n_sel, pitch, P[g], ldp)
+        eng.fft_sed(P, len(entries), group_stride, nk, n_t, ldp, mode, out, n_k, k0)
+    return out

@@ -1,0 +1,65 @@
+"""The C-ABI library must build, load on a CPU-only box, and export every symbol the header declares
+(no compute call is made here - that needs a GPU)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as entry
+    entry.build()
+    from psa_b200 import _lib
+    return _lib.load()
+
+
+def _declared():
+    text = (ROOT / "include" / "psa_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(psa_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from psa_b200 import _lib
+    names = _declared()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/psa_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == names, "ctypes signature table and header disagree"
+
+
+def test_version_error_and_pitch_need_no_gpu(lib):
+    assert lib.psa_version() >= 100
+    assert isinstance(lib.psa_last_error(), bytes)
+    assert lib.psa_pitch(1) == 64 and lib.psa_pitch(64) == 64 and lib.psa_pitch(65) == 128
+    assert lib.psa_pitch(4096) == 4096
+
+
+def test_bad_arguments_are_reported_not_crashed(lib):
+    from psa_b200 import _lib
+    # argument validation happens before any CUDA call, so this is safe without a device
+    status = lib.psa_project(None, 0, 0, None, None, 0, 0, 0, None, 0, 0, None)
+    assert status == _lib.ERR_BAD_ARG and b"psa_project" in lib.psa_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(lib.psa_digitize(None, None, None, 1, 1, 1, 64, None, None, None))
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from psa_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setenv("PSA_B200_LIB", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+    monkeypatch.delenv("PSA_B200_LIB")
+    monkeypatch.setattr(_lib, "_lib", None)
+    _lib.load()
+
+
+def test_product_code_never_imports_the_oracle():
+    for path in (ROOT / "psa_b200").rglob("*.py"):
+        text = path.read_text()
+        assert "oracle" not in re.sub(r'""".*?"""', "", text, flags=re.S).replace("# oracle", ""), path

@@ -1,0 +1,422 @@
+"""Parity tests proper: every CUDA kernel, called through the C ABI, against (1) the bit-exact
+integer model, (2) the oracle, (3) the golden outputs of the real reference.  Run with `-m gpu`."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+import intmodel as M  # noqa: E402
+from oracle import psa_oracle as O  # noqa: E402
+from psa_b200 import synth  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from psa_b200 import _lib
+    from psa_b200.engine import Engine
+    assert _lib.load().psa_version() >= 100
+    return Engine()
+
+
+def dev(eng, arr):
+    return torch.from_numpy(np.ascontiguousarray(arr)).to(eng.device)
+
+
+# ------------------------------------------------------------------ ingest
+@pytest.mark.parametrize("n_t,n_a", [(256, 64), (3001, 37), (17, 1000)])
+def test_mean_positions_bit_exact(eng, n_t, n_a):
+    rng = np.random.default_rng(n_t)
+    pos = (rng.random((n_t, n_a, 3)) * 43.4 + rng.standard_normal((n_t, n_a, 3)) * 0.01).astype(np.float32)
+    got = eng.mean_positions(dev(eng, pos)).cpu().numpy()
+    np.testing.assert_array_equal(got, np.mean(pos, axis=0, dtype=np.float32))
+
+
+@pytest.mark.parametrize("case", ["all", "subset", "displacement", "zeros"])
+def test_digitize_exact(eng, case):
+    rng = np.random.default_rng(5)
+    n_t, n_a = 33, 203
+    data = (rng.standard_normal((n_t, n_a, 3)) * np.array([3.0, 0.02, 700.0])).astype(np.float32)
+    idx, mean = None, None
+    if case == "subset":
+        idx = np.array([5, 0, 77, 77, 202, 13, 14, 15, 100], np.int32)
+    if case == "displacement":
+        mean = (rng.random((n_a, 3)) * 3).astype(np.float32)
+    if case == "zeros":
+        data[:, :, 1] = 0.0
+        data[7] = 0.0
+    sel = data if idx is None else data[:, idx, :]
+    if mean is not None:
+        sel = sel - mean[None]
+    n_sel = sel.shape[1]
+    dig, expo, pitch = eng.digitize(dev(eng, data), None if mean is None else dev(eng, mean),
+                                    None if idx is None else dev(eng, idx), n_sel)
+    x_ref, e_ref = M.digitize(sel)
+    np.testing.assert_array_equal(expo.cpu().numpy(), e_ref)
+    d = dig.cpu().numpy()                                     # (3, 4, n_t, pitch)
+    assert pitch % 64 == 0 and pitch >= n_sel
+    assert not d[:, :, :, n_sel:].any()                       # padding is zero
+    for pol in range(3):
+        np.testing.assert_array_equal(d[pol, :, :, :n_sel], M.balanced_digits(x_ref[pol]))
+
+
+def test_phase_digits(eng):
+    rng = np.random.default_rng(6)
+    n_a, n_k = 500, 23
+    mean = (rng.random((n_a, 3)) * 43.0).astype(np.float32)
+    kv = (rng.standard_normal((n_k, 3)) * 2.5).astype(np.float32)
+    kv[0] = 0.0                                                # Gamma: cos = 1 exactly, sin = 0
+    idx = rng.permutation(n_a)[:301].astype(np.int32)
+    for sel_idx in (None, idx):
+        msel = mean if sel_idx is None else mean[sel_idx]
+        n_sel = msel.shape[0]
+        pitch = -(-n_sel // 64) * 64
+        rows_alloc = 2 * n_k + 6
+        ad = eng.phase_digits(dev(eng, kv), dev(eng, mean), None if sel_idx is None else dev(eng, sel_idx),
+                              n_sel, pitch, rows_alloc).cpu().numpy()
+        got = M.digits_to_int(ad[:, :2 * n_k, :n_sel])
+        want = M.phase_ints(kv, msel)
+        assert got[0].min() == got[0].max() == 2 ** 30 and not got[1].any()
+        diff = np.abs(got - want)
+        assert (diff == 0).mean() > 0.995, (diff == 0).mean()   # rest: fma-vs-sgemm / double-rounding corner cases
+        assert diff.max() <= 2 ** 8, diff.max()                 # at most a few float32 ulps of a value near 1
+        assert not ad[:, :2 * n_k, n_sel:].any()
+
+
+# ------------------------------------------------------------------ projection
+def _proj_inputs(rng, rows, n_t, n_sel):
+    xa = rng.integers(-2 ** 30, 2 ** 30, (rows, n_sel), endpoint=True)
+    xb = rng.integers(-2 ** 30 + 1, 2 ** 30, (3, n_t, n_sel))
+    e = rng.integers(-12, 9, (3, n_t)).astype(np.int32)
+    return xa, xb, e
+
+
+def _run_project(eng, xa, xb, e, impl, rows_alloc=None):
+    from psa_b200 import _lib
+    rows, n_sel = xa.shape
+    n_t = xb.shape[1]
+    pitch = -(-n_sel // 64) * 64
+    rows_alloc = rows_alloc or rows
+    ad = np.zeros((4, rows_alloc, pitch), np.int8)
+    ad[:, :rows, :n_sel] = M.balanced_digits(xa)
+    bd = np.zeros((3, 4, n_t, pitch), np.int8)
+    for pol in range(3):
+        bd[pol, :, :, :n_sel] = M.balanced_digits(xb[pol])
+    ldp = -(-n_t // 4) * 4
+    P = torch.full((rows, 3, ldp), float("nan"), dtype=torch.float32, device=eng.device)
+    eng.project(dev(eng, ad), rows, rows_alloc, dev(eng, bd), dev(eng, e), n_t, n_sel, pitch, P, ldp, impl=impl)
+    torch.cuda.synchronize()
+    return P.cpu().numpy()[:, :, :n_t]
+
+
+SHAPES = [(2, 16, 64), (24, 128, 64), (128, 128, 256), (200, 300, 1000), (130, 77, 65), (256, 512, 4096)]
+
+
+@pytest.mark.parametrize("rows,n_t,n_sel", SHAPES)
+def test_project_simt_matches_integer_model(eng, rows, n_t, n_sel):
+    from psa_b200 import _lib
+    xa, xb, e = _proj_inputs(np.random.default_rng(rows + n_t), rows, n_t, n_sel)
+    got = _run_project(eng, xa, xb, e, _lib.PROJECT_SIMT, rows_alloc=rows + 10)
+    np.testing.assert_array_equal(got, M.project(xa, xb, e))
+
+
+@pytest.mark.parametrize("rows,n_t,n_sel", SHAPES)
+def test_project_tensor_matches_integer_model(eng, rows, n_t, n_sel):
+    from psa_b200 import _lib
+    xa, xb, e = _proj_inputs(np.random.default_rng(rows * 3 + n_t), rows, n_t, n_sel)
+    got = _run_project(eng, xa, xb, e, _lib.PROJECT_TENSOR, rows_alloc=rows + 10)
+    np.testing.assert_array_equal(got, M.project(xa, xb, e))
+
+
+def test_project_extreme_digits_no_overflow(eng):
+    """Worst-case digits (every product at its maximum) over a full 32768-atom pass stay exact."""
+    from psa_b200 import _lib
+    n_sel, rows, n_t = 32768 + 64, 2, 16
+    worst = -128 * (1 + 256 + 65536) - 64 * 2 ** 24            # digits (-128, -128, -128, -64)
+    xa = np.full((rows, n_sel), worst, np.int64)
+    xb = np.full((3, n_t, n_sel), worst, np.int64)
+    xa[1] = -worst - 2 * 128 * (1 + 256 + 65536)                 # digits (-128, -128, -128, +64)
+    e = np.zeros((3, n_t), np.int32)
+    want = M.project(xa, xb, e)
+    for impl in (_lib.PROJECT_SIMT, _lib.PROJECT_TENSOR):
+        np.testing.assert_array_equal(_run_project(eng, xa, xb, e, impl), want)
+
+
+def test_project_two_pass_accumulation(eng):
+    from psa_b200 import _lib
+    rows, n_t, n_sel = 6, 32, 40000
+    xa, xb, e = _proj_inputs(np.random.default_rng(99), rows, n_t, n_sel)
+    want = M.project(xa, xb, e)
+    for impl in (_lib.PROJECT_SIMT, _lib.PROJECT_TENSOR):
+        np.testing.assert_array_equal(_run_project(eng, xa, xb, e, impl), want)
+
+
+# ------------------------------------------------------------------ FFT + assembly
+@pytest.mark.parametrize("n_t", [16, 32, 64, 1024, 2048, 16384, 32768, 65536])
+def test_fft_coherent(eng, n_t):
+    rng = np.random.default_rng(n_t)
+    n_k, n_k_total, k_off = 3, 5, 1
+    ldp = n_t
+    P = rng.standard_normal((2 * n_k, 3, ldp)).astype(np.float32)
+    out = torch.zeros((n_t, n_k_total, 3), dtype=torch.complex64, device=eng.device)
+    eng.fft_sed(dev(eng, P), 1, P.size, n_k, n_t, ldp, 0, out, n_k_total, k_off)
+    got = out.cpu().numpy()
+    z = (P[0::2].astype(np.float64) + 1j * P[1::2].astype(np.float64))          # (n_k, 3, n_t)
+    want = (np.fft.fft(z, axis=-1) / n_t).transpose(2, 0, 1)
+    scale = np.abs(want).max()
+    assert np.abs(got[:, k_off:k_off + n_k, :] - want).max() < 3e-6 * scale
+    assert not got[:, 0, :].any() and not got[:, 4, :].any()                     # untouched k columns
+
+
+@pytest.mark.parametrize("n_t", [64, 2048, 32768])
+def test_fft_incoherent(eng, n_t):
+    rng = np.random.default_rng(n_t + 1)
+    n_k, groups = 4, 3
+    P = rng.standard_normal((groups, 2 * n_k, 3, n_t)).astype(np.float32)
+    out = torch.zeros((n_t, n_k), dtype=torch.float32, device=eng.device)
+    eng.fft_sed(dev(eng, P), groups, P[0].size, n_k, n_t, n_t, 1, out, n_k, 0)
+    z = P[:, 0::2].astype(np.float64) + 1j * P[:, 1::2].astype(np.float64)      # (g, n_k, 3, n_t)
+    want = (np.abs(np.fft.fft(z, axis=-1) / n_t) ** 2).sum(axis=(0, 2)).T
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=2e-5, atol=1e-6 * want.max())
+
+
+def test_fft_rejects_unsupported_length(eng):
+    out = torch.zeros((250, 1, 3), dtype=torch.complex64, device=eng.device)
+    with pytest.raises(NotImplementedError):
+        eng.fft_sed(torch.zeros((2, 3, 252), device=eng.device), 1, 0, 1, 250, 252, 0, out, 1, 0)
+
+
+# ------------------------------------------------------------------ element-wise kernels
+def test_chiral_and_intensity_kernels(eng, gold_gr):
+    sed = gold_gr["sed_coh"]
+    d = dev(eng, sed)
+    inten = eng.intensity(d).cpu().numpy()
+    np.testing.assert_allclose(inten, O.intensity(sed), rtol=3e-7)
+    n = sed.shape[0] * sed.shape[1]
+    flat = torch.view_as_real(d).view(-1, 2)
+    strong = O.intensity(sed) > 1e-8 * O.intensity(sed).max()
+    for axis, (i, j) in (("x", (1, 2)), ("y", (0, 2)), ("z", (0, 1))):
+        out = eng.empty(sed.shape[:2], torch.float32)
+        eng.chiral_phase(flat[i:], flat[j:], n, 3, 3, "C", out)
+        got, want = out.cpu().numpy(), gold_gr[f"phase_C_{axis}"]
+        assert np.abs(got - want)[strong].max() < 2e-5
+        assert np.abs(got).max() <= np.pi / 2 + 1e-6
+    for opt in "AB":
+        out = eng.empty(sed.shape[:2], torch.float32)
+        eng.chiral_phase(flat[0:], flat[1:], n, 3, 3, opt, out)
+        assert np.median(np.abs(out.cpu().numpy() - gold_gr[f"phase_{opt}_z"])) < 1e-6
+
+
+# ------------------------------------------------------------------ whole path vs the real reference's outputs
+def _calc(g, **kw):
+    from psa_b200 import SEDCalculator, Trajectory
+    box = g["box_matrix"]
+    traj = Trajectory(g["positions"], g["velocities"], g["types"], np.arange(g["positions"].shape[0]), box,
+                      np.diag(box).copy(), np.zeros(3, np.float32), float(g["dt_ps"]))
+    return SEDCalculator(traj, *[int(c) for c in g["cells"]], **kw)
+
+
+GOLD_CASES = {
+    "coh_all_100": ("kpath_100_vecs", {}),
+    "coh_all_110": ("kpath_110_vecs", {}),
+    "coh_all_111": ("kpath_111_vecs", {}),
+    "coh_all_100_chunk5": ("kpath_100_vecs", dict(k_chunk_size=5)),
+    "coh_types12": ("kpath_110_vecs", dict(basis_atom_types=[1, 2], summation_mode="coherent")),
+    "inc_types12": ("kpath_110_vecs", dict(basis_atom_types=[1, 2], summation_mode="incoherent")),
+    "inc_types1": ("kpath_110_vecs", dict(basis_atom_types=[1], summation_mode="incoherent")),
+    "inc_types_nested": ("kpath_110_vecs", dict(basis_atom_types=[[1, 2]], summation_mode="incoherent")),
+    "inc_types_unknown": ("kpath_100_vecs", dict(basis_atom_types=[7], summation_mode="incoherent")),
+    "inc_types_1_and_unknown": ("kpath_100_vecs", dict(basis_atom_types=[1, 7], summation_mode="incoherent")),
+    "inc_indices": ("kpath_100_vecs", dict(basis_atom_indices=[[0, 1, 5, 9], [2, 3, 40]], summation_mode="incoherent")),
+    "coh_indices_union": ("kpath_100_vecs", dict(basis_atom_indices=[[0, 1, 5, 9], [2, 3, 5]])),
+    "coh_indices_flat_dup": ("kpath_100_vecs", dict(basis_atom_indices=[3, 1, 1, 20])),
+    "coh_indices_ndarray": ("kpath_100_vecs", dict(basis_atom_indices=np.array([4, 8, 15, 16, 23, 42]))),
+    "inc_all": ("kpath_100_vecs", dict(summation_mode="incoherent")),
+    "kgrid_xy": ("kgrid_xy_vecs", dict(k_grid_shape=(4, 3))),
+}
+
+
+@pytest.mark.parametrize("name", sorted(GOLD_CASES))
+def test_calculate_matches_reference_outputs(gold_si, name):
+    kkey, kw = GOLD_CASES[name]
+    calc = _calc(gold_si)
+    kv = gold_si[kkey]
+    res = calc.calculate(np.zeros(len(kv), np.float32), kv, **kw)
+    ref = gold_si[f"sed_{name}"]
+    assert res.sed.shape == ref.shape and res.sed.dtype == ref.dtype
+    assert res.is_complex == bool(gold_si[f"cplx_{name}"])
+    np.testing.assert_array_equal(res.freqs, gold_si["freqs"])
+    # float32 noise of the reference itself is ~1e-6 of the peak at this size
+    if res.is_complex:
+        assert np.abs(res.sed - ref).max() < 2e-6 * np.abs(ref).max()
+    else:
+        np.testing.assert_allclose(res.sed, ref, rtol=0, atol=4e-6 * ref.max())
+    assert res["sed"] is res.sed and res.k_grid_shape == kw.get("k_grid_shape")
+
+
+def test_displacement_mode_matches_reference(gold_si):
+    calc = _calc(gold_si, use_displacements=True)
+    kv = gold_si["kpath_100_vecs"]
+    ref = gold_si["sed_disp_coh_all_100"]
+    res = calc.calculate(gold_si["kpath_100_mags"], kv)
+    assert np.abs(res.sed - ref).max() < 2e-6 * np.abs(ref).max()
+    ref2 = gold_si["sed_disp_inc_types12"]
+    res2 = calc.calculate(gold_si["kpath_110_mags"], gold_si["kpath_110_vecs"], basis_atom_types=[1, 2],
+                          summation_mode="incoherent")
+    np.testing.assert_allclose(res2.sed, ref2, rtol=0, atol=4e-6 * ref2.max())
+
+
+def test_api_errors_and_edge_cases(gold_si):
+    calc = _calc(gold_si)
+    kv = gold_si["kpath_100_vecs"]
+    with pytest.raises(ValueError):
+        calc.calculate(np.zeros(len(kv)), kv, summation_mode="both")
+    with pytest.raises(ValueError):
+        calc.calculate(np.zeros(len(kv)), kv, basis_atom_indices=[0, 10 ** 6])
+    empty = calc.calculate(np.zeros(0, np.float32), np.zeros((0, 3), np.float32))
+    assert empty.sed.shape == (256, 0, 3) and empty.sed.dtype == np.complex64
+    one = calc.calculate(np.zeros(1, np.float32), kv[3:4])
+    assert np.abs(one.sed[:, 0] - gold_si["sed_coh_all_100"][:, 3]).max() < 2e-6 * np.abs(gold_si["sed_coh_all_100"]).max()
+    # intensity property of the result type (reference sed.py:22-24)
+    np.testing.assert_allclose(calc.calculate(np.zeros(len(kv)), kv).intensity, gold_si["intensity_coh_all_100"],
+                               rtol=1e-4, atol=1e-6 * gold_si["intensity_coh_all_100"].max())
+
+
+def test_chunk_invariance_is_bitwise(gold_si):
+    calc = _calc(gold_si)
+    kv = gold_si["kpath_110_vecs"]
+    a = calc.calculate(np.zeros(len(kv)), kv, k_chunk_size=500).sed
+    b = calc.calculate(np.zeros(len(kv)), kv, k_chunk_size=5).sed
+    np.testing.assert_array_equal(a, b)
+
+
+def test_chiral_sed_facade(gold_gr):
+    calc = _calc(gold_gr)
+    res = calc.calculate_chiral_sed([1, 0, 0], bz_coverage=4.0, n_k=10, chiral_axis="z")
+    ref = gold_gr["sed_coh"]
+    assert np.abs(res.sed - ref).max() < 2e-6 * np.abs(ref).max()
+    strong = O.intensity(ref) > 1e-6 * O.intensity(ref).max()
+    assert np.abs(res.phase - gold_gr["phase_C_z"])[strong].max() < 1e-3
+    assert res.phase.dtype == np.float32 and res.phase.shape == ref.shape[:2]
+    # the public method on host arrays
+    ph = calc.calculate_chiral_phase(ref[:, :, 0], ref[:, :, 1], "C")
+    assert np.abs(ph - gold_gr["phase_C_z"])[strong].max() < 2e-5
+    with pytest.raises(ValueError):
+        calc.calculate_chiral_phase(ref[:, :, 0], ref[:, :3, 1])
+
+
+def test_kgrid_and_kpath_facades(gold_si):
+    calc = _calc(gold_si)
+    res = calc.calculate_kgrid_sed("xy", (-1.5, 2.0, -0.5, 1.0), 4, 3, 0.25)
+    assert res.k_grid_shape == (4, 3) and res.k_points.size == 0
+    ref = gold_si["sed_kgrid_xy"]
+    assert np.abs(res.sed - ref).max() < 2e-6 * np.abs(ref).max()
+    res = calc.calculate_kpath_sed([1, 1, 0], 4.0, 12, basis_atom_types=[1, 2], summation_mode="incoherent")
+    np.testing.assert_allclose(res.sed, gold_si["sed_inc_types12"], rtol=0, atol=4e-6 * gold_si["sed_inc_types12"].max())
+    assert not res.is_complex and res["is_complex"] is False
+
+
+def test_ised_matches_reference(gold_si, tmp_path):
+    calc = _calc(gold_si)
+    common = dict(char_len_k_path=5.431, nk_on_path=9, bz_cov_ised=1.0, n_recon_frames=8)
+    kt, wt = float(gold_si["ised_k_target"]), float(gold_si["ised_w_target"])
+    out = calc.reconstruct([1, 0, 0], [(kt, wt)], basis_atom_types_ised=[1, 2], rescale_factor=0.5, **common)
+    assert np.abs(out[0]["frames"] - gold_si["ised_types_float"]).max() < 2e-5
+    out = calc.reconstruct([1, 0, 0], [(kt, wt)], rescale_factor="auto", **common)
+    assert np.abs(out[0]["frames"] - gold_si["ised_all_auto"]).max() < 2e-5
+    out = calc.reconstruct([1, 0, 0], [(0.3, wt * 0.5)], basis_atom_idx_ised=[[0, 1, 2, 3], [10, 11, 12]],
+                           rescale_factor="auto", **common)
+    assert np.abs(out[0]["frames"] - gold_si["ised_idx_auto"]).max() < 2e-5
+    # batched call == single calls; dump file round trip
+    both = calc.reconstruct([1, 0, 0], [(kt, wt), (0.3, wt * 0.5)], rescale_factor=0.5, **common)
+    single = calc.reconstruct([1, 0, 0], [(0.3, wt * 0.5)], rescale_factor=0.5, **common)
+    np.testing.assert_array_equal(both[1]["frames"], single[0]["frames"])
+    dump = tmp_path / "m.dump"
+    calc.ised([1, 0, 0], kt, wt, rescale_factor=0.5, dump_filepath=str(dump), **common)
+    text = dump.read_text().splitlines()
+    assert text[0] == "ITEM: TIMESTEP" and text[3] == str(len(gold_si["types"]))
+    assert len(text) == 8 * (9 + len(gold_si["types"]))
+
+
+def test_ised_reconstructor_facade(gold_si, tmp_path):
+    from psa_b200 import iSEDReconstructor
+    calc = _calc(gold_si)
+    res = calc.calculate_kpath_sed([1, 0, 0], 1.0, 9, lat_param=5.431)
+    rec = iSEDReconstructor(res)
+    motion = rec.reconstruct_motion(float(gold_si["ised_k_target"]), float(gold_si["ised_w_target"]),
+                                    n_frames=8, rescale_factor="auto")
+    assert np.abs(motion - gold_si["ised_all_auto"]).max() < 2e-5
+    rec.save_trajectory(motion, str(tmp_path / "x.dump"))
+    assert (tmp_path / "x.dump").exists()
+
+
+def test_odd_frame_count_is_reported_not_faked(gold_si):
+    from psa_b200 import SEDCalculator, Trajectory
+    g = gold_si
+    box = g["box_matrix"]
+    traj = Trajectory(g["positions"][:250], g["velocities"][:250], g["types"], np.arange(250), box,
+                      np.diag(box).copy(), np.zeros(3, np.float32), float(g["dt_ps"]))
+    calc = SEDCalculator(traj, 2, 2, 2)
+    with pytest.raises(NotImplementedError):
+        calc.calculate(g["kpath_100_mags"], g["kpath_100_vecs"])
+
+
+# ------------------------------------------------------------------ medium size: three-distance parity report
+def test_three_distance_parity_medium():
+    from psa_b200 import SEDCalculator
+    spec = synth.si_spec("mid", n_cells=4, n_frames=2048, seed=21)
+    traj = spec.trajectory()
+    calc = SEDCalculator(traj, *spec.cells)
+    for direction in ([1, 0, 0], [1, 1, 0]):
+        mags, kv = calc.get_k_path(direction, 4.0, 48)
+        new = calc.calculate(mags, kv)
+        ref = O.calculate(traj.positions, traj.velocities, traj.types, traj.dt_ps, kv)
+        o64 = O.calculate_fp64(traj.positions, traj.velocities, traj.types, traj.dt_ps, kv)
+        i_new, i_ref = O.intensity(new.sed).astype(np.float64), O.intensity(ref["sed"]).astype(np.float64)
+        i_64 = np.sum(np.abs(o64["sed"]) ** 2, axis=-1)
+        rep = O.parity_report(i_new, i_ref, i_64)
+        print(direction, {t: {k: f"{v['max']:.2e}" for k, v in rep[t].items()} for t in (1e-4, 1e-5, 1e-6)})
+        assert rep["global_peak_equal"] and rep["per_k_peak_equal"]
+        # against the float64 truth the CUDA path is well inside the north-star tolerance ...
+        assert rep[1e-6]["new_o64"]["max"] < 1e-5
+        # ... and against the reference it is limited by the reference's own float32 floor
+        floor = rep[1e-6]["ref_o64"]["max"]
+        assert rep[1e-6]["new_ref"]["max"] < max(1e-5, 1.5 * floor)
+        assert rep[1e-4]["new_ref"]["max"] < 1e-5
+        assert rep[1e-6]["new_o64"]["max"] <= floor                      # never worse than the reference
+
+
+# ------------------------------------------------------------------ BASELINE config 1 at full size: properties
+def test_full_size_config1_properties():
+    from psa_b200 import SEDCalculator, _lib
+    from psa_b200.engine import Engine
+    cfg = synth.baseline_config("c1")
+    spec = cfg["spec"]
+    traj = spec.trajectory()
+    calc = SEDCalculator(traj, *spec.cells)
+    mags, kv = calc.get_k_path([1, 0, 0], 4.0, 100)
+    res = calc.calculate(mags, kv)
+    assert res.sed.shape == (8192, 100, 3)
+    # (a) the Gamma-point column is the FFT of the total velocity: an O(n_t n_a) host computation
+    tot = traj.velocities.astype(np.float64).sum(axis=1)
+    want0 = np.fft.fft(tot, axis=0) / tot.shape[0]
+    assert np.abs(res.sed[:, 0, :] - want0).max() < 5e-7 * np.abs(want0).max()
+    # (b) dispersion peak of the strongest planted mode sits where it was planted (frequency bin)
+    inten = res.intensity
+    f_pk, k_pk = np.unravel_index(np.argmax(inten[: 4096]), inten[: 4096].shape)
+    df = 1.0 / (8192 * spec.dt_ps)
+    assert np.min(np.abs(spec.freq - f_pk * df)) <= df
+    # (c) tensor-core and CUDA-core projection agree bit for bit at full size (k subset)
+    calc_s = SEDCalculator(traj, *spec.cells)
+    calc_s._engine = Engine(project_impl=_lib.PROJECT_SIMT)
+    sub = calc_s.calculate(mags[40:48], kv[40:48])
+    np.testing.assert_array_equal(sub.sed, res.sed[:, 40:48, :])
+    # (d) linearity in the atom selection: S(all) = S(type 1) + S(type 2) up to float32 rounding
+    s1 = calc.calculate(mags[:16], kv[:16], basis_atom_types=[1]).sed.astype(np.complex128)
+    s2 = calc.calculate(mags[:16], kv[:16], basis_atom_types=[2]).sed.astype(np.complex128)
+    assert np.abs(s1 + s2 - res.sed[:, :16, :]).max() < 1e-6 * np.abs(res.sed[:, :16, :]).max()
