@@ -196,7 +196,7 @@ def test_chiral_and_intensity_kernels(eng, gold_gr):
     sed = gold_gr["sed_coh"]
     d = dev(eng, sed)
     inten = eng.intensity(d).cpu().numpy()
-    np.testing.assert_allclose(inten, O.intensity(sed), rtol=3e-7)
+    np.testing.assert_allclose(inten, O.intensity(sed), rtol=1e-6)
     n = sed.shape[0] * sed.shape[1]
     flat = torch.view_as_real(d).view(-1, 2)
     strong = O.intensity(sed) > 1e-8 * O.intensity(sed).max()
