@@ -45,6 +45,7 @@ class Engine:
         self.project_impl = project_impl
         self._twiddles: Dict[int, torch.Tensor] = {}
         self.launches = 0          # kernels launched through this engine (bench reports it)
+        self.profile: Optional[Dict[str, List[Tuple[torch.cuda.Event, torch.cuda.Event, int]]]] = None
 
     # -- helpers
     def stream(self) -> int:
@@ -53,12 +54,33 @@ class Engine:
     def empty(self, shape, dtype) -> torch.Tensor:
         return torch.empty(shape, dtype=dtype, device=self.device)
 
+    def _run(self, kernel: str, n_launches: int, *args) -> None:
+        """One C-ABI call; with ``self.profile`` set, bracketed by CUDA events on the launching stream."""
+        self.launches += n_launches
+        if self.profile is None:
+            _lib.call(kernel, *args)
+            return
+        stream = torch.cuda.current_stream(self.device)
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(stream)
+        _lib.call(kernel, *args)
+        end.record(stream)
+        self.profile.setdefault(kernel, []).append((start, end, n_launches))
+
+    def profile_summary(self) -> Dict[str, Dict[str, float]]:
+        """{kernel: {ms, calls, launches}} from the events collected while ``self.profile`` was set."""
+        torch.cuda.synchronize(self.device)
+        out: Dict[str, Dict[str, float]] = {}
+        for name, evs in (self.profile or {}).items():
+            out[name] = dict(ms=sum(a.elapsed_time(b) for a, b, _ in evs), calls=len(evs),
+                             launches=sum(n for _, _, n in evs))
+        return out
+
     # -- kernels
     def mean_positions(self, pos: torch.Tensor) -> torch.Tensor:
         n_t, n_a, _ = pos.shape
         mean = self.empty((n_a, 3), torch.float32)
-        _lib.call("psa_mean_positions", pos.data_ptr(), n_t, n_a, mean.data_ptr(), self.stream())
-        self.launches += 1
+        self._run("psa_mean_positions", 1, pos.data_ptr(), n_t, n_a, mean.data_ptr(), self.stream())
         return mean
 
     def digitize(self, data: torch.Tensor, mean: Optional[torch.Tensor], idx: Optional[torch.Tensor],
@@ -67,9 +89,8 @@ class Engine:
         pitch = int(_lib.load().psa_pitch(n_sel))
         dig = self.empty((3, 4, n_t, pitch), torch.int8)
         expo = self.empty((3, n_t), torch.int32)
-        _lib.call("psa_digitize", data.data_ptr(), _ptr(mean), _ptr(idx), n_t, n_a, n_sel, pitch,
+        self._run("psa_digitize", 1, data.data_ptr(), _ptr(mean), _ptr(idx), n_t, n_a, n_sel, pitch,
                   dig.data_ptr(), expo.data_ptr(), self.stream())
-        self.launches += 1
         return dig, expo, pitch
 
     def phase_digits(self, kvecs: torch.Tensor, mean: torch.Tensor, idx: Optional[torch.Tensor], n_sel: int,
@@ -77,45 +98,40 @@ class Engine:
         n_k = kvecs.shape[0]
         if out is None:
             out = self.empty((4, rows_alloc, pitch), torch.int8)
-        _lib.call("psa_phase_digits", kvecs.data_ptr(), n_k, mean.data_ptr(), _ptr(idx), n_sel, pitch,
+        self._run("psa_phase_digits", 1, kvecs.data_ptr(), n_k, mean.data_ptr(), _ptr(idx), n_sel, pitch,
                   rows_alloc, out.data_ptr(), self.stream())
-        self.launches += 1
         return out
 
     def project(self, adig: torch.Tensor, rows: int, rows_alloc: int, bdig: torch.Tensor, expo: torch.Tensor,
                 n_t: int, n_sel: int, pitch: int, P: torch.Tensor, ldp: int, impl: Optional[int] = None) -> None:
-        _lib.call("psa_project", adig.data_ptr(), rows, rows_alloc, bdig.data_ptr(), expo.data_ptr(), n_t, n_sel,
-                  pitch, P.data_ptr(), ldp, self.project_impl if impl is None else impl, self.stream())
-        self.launches += -(-n_sel // 32768)
+        self._run("psa_project", -(-n_sel // 32768), adig.data_ptr(), rows, rows_alloc, bdig.data_ptr(),
+                  expo.data_ptr(), n_t, n_sel, pitch, P.data_ptr(), ldp,
+                  self.project_impl if impl is None else impl, self.stream())
 
     def twiddles(self, n_t: int) -> torch.Tensor:
         tw = self._twiddles.get(n_t)
         if tw is None:
             tw = self.empty((n_t, 2), torch.float32)
-            _lib.call("psa_twiddles", n_t, tw.data_ptr(), self.stream())
-            self.launches += 1
+            self._run("psa_twiddles", 1, n_t, tw.data_ptr(), self.stream())
             self._twiddles[n_t] = tw
         return tw
 
     def fft_sed(self, P: torch.Tensor, n_groups: int, group_stride: int, n_k: int, n_t: int, ldp: int,
                 mode: int, out: torch.Tensor, n_k_total: int, k_offset: int) -> None:
         tw = self.twiddles(n_t)
-        _lib.call("psa_fft_sed", P.data_ptr(), n_groups, group_stride, n_k, n_t, ldp, tw.data_ptr(), mode,
+        self._run("psa_fft_sed", 1, P.data_ptr(), n_groups, group_stride, n_k, n_t, ldp, tw.data_ptr(), mode,
                   out.data_ptr(), n_k_total, k_offset, self.stream())
-        self.launches += 1
 
     def chiral_phase(self, z1: torch.Tensor, z2: torch.Tensor, n: int, stride1: int, stride2: int, opt: str,
                      out: torch.Tensor) -> None:
-        _lib.call("psa_chiral_phase", z1.data_ptr(), z2.data_ptr(), n, stride1, stride2, ord(opt),
+        self._run("psa_chiral_phase", 1, z1.data_ptr(), z2.data_ptr(), n, stride1, stride2, ord(opt),
                   out.data_ptr(), self.stream())
-        self.launches += 1
 
     def intensity(self, sed: torch.Tensor) -> torch.Tensor:
         n_pol = sed.shape[-1]
         n_rows = sed.numel() // n_pol
         out = self.empty(sed.shape[:-1], torch.float32)
-        _lib.call("psa_intensity", sed.data_ptr(), n_rows, n_pol, out.data_ptr(), self.stream())
-        self.launches += 1
+        self._run("psa_intensity", 1, sed.data_ptr(), n_rows, n_pol, out.data_ptr(), self.stream())
         return out
 
 
@@ -177,6 +193,12 @@ class DeviceTrajectory:
     def release(self, which: str) -> None:
         self._dev.pop(which, None)
 
+    def reset_derived(self) -> None:
+        """Forget mean positions and digit planes (keeps the raw trajectory resident)."""
+        with self._lock:
+            self._mean = None
+            self._groups.clear()
+
     @property
     def mean(self) -> torch.Tensor:
         with self._lock:
@@ -184,13 +206,30 @@ class DeviceTrajectory:
                 self._mean = self.engine.mean_positions(self.positions)
             return self._mean
 
-    def group(self, idx: Optional[np.ndarray], use_displacements: bool) -> Tuple:
-        """``(idx_dev|None, n_sel, pitch, digits, exponents)`` for an atom selection (cached)."""
+    def _group_key(self, idx: Optional[np.ndarray], use_displacements: bool) -> Tuple[Tuple, Optional[np.ndarray]]:
         if idx is not None and idx.size == self.n_a and np.array_equal(idx, np.arange(self.n_a)):
             idx = None
-        key = (use_displacements,
-               None if idx is None else hashlib.blake2b(np.ascontiguousarray(idx, np.int64).tobytes(),
-                                                         digest_size=16).hexdigest())
+        digest = None if idx is None else hashlib.blake2b(np.ascontiguousarray(idx, np.int64).tobytes(),
+                                                          digest_size=16).hexdigest()
+        return (use_displacements, digest), idx
+
+    def install_mean(self, mean: torch.Tensor) -> None:
+        """Adopt mean positions computed elsewhere (multi-GPU: broadcast from the source rank)."""
+        with self._lock:
+            self._mean = mean
+
+    def install_group(self, idx: Optional[np.ndarray], use_displacements: bool, dig: torch.Tensor,
+                      expo: torch.Tensor) -> None:
+        """Adopt digit planes computed elsewhere for the atom selection ``idx``."""
+        key, idx = self._group_key(idx, use_displacements)
+        idx_dev = None if idx is None else torch.from_numpy(np.ascontiguousarray(idx, np.int32)).to(self.engine.device)
+        n_sel = self.n_a if idx is None else int(idx.size)
+        with self._lock:
+            self._groups[key] = (idx_dev, n_sel, int(dig.shape[-1]), dig, expo)
+
+    def group(self, idx: Optional[np.ndarray], use_displacements: bool) -> Tuple:
+        """``(idx_dev|None, n_sel, pitch, digits, exponents)`` for an atom selection (cached)."""
+        key, idx = self._group_key(idx, use_displacements)
         with self._lock:
             hit = self._groups.get(key)
             if hit is not None:
