@@ -83,7 +83,7 @@ int psa_twiddles(int64_t n, float* tw, void* stream);
  *   tw  psa_twiddles(n_t)
  *   out coherent: complex64 [n_t][n_k_total][3], this call fills k in [k_offset, k_offset+n_k)
  *       incoherent: float32 [n_t][n_k_total]
- * n_t must be a power of two >= 16 in this version. */
+ * n_t must be a power of two >= 32 in this version. */
 int psa_fft_sed(const float* P, int64_t n_groups, int64_t group_stride, int64_t n_k, int64_t n_t,
                 int64_t ldp, const float* tw, int mode, void* out, int64_t n_k_total, int64_t k_offset,
                 void* stream);

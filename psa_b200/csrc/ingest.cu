@@ -8,34 +8,65 @@ namespace psa {
 // Mean position.  np.mean(positions, axis=0, dtype=float32) reduces the OUTER axis of a
 // C-contiguous array, i.e. one sequential float32 accumulation per (atom, xyz) column in frame
 // order, followed by a float32 division (reference: sed_calculator.py:205; recipe verified in
-// SURVEY.md appendix A).  One thread owns one column; loads are issued in independent batches so
-// only the adds are serial.
+// SURVEY.md appendix A).
 // ---------------------------------------------------------------------------------------------
-constexpr int kMeanBatch = 16;
+// The adds of one column are inherently serial, so bandwidth has to come from memory-level
+// parallelism instead: a CTA owns 32 adjacent columns (one 128-byte line per frame); all 8 warps
+// stream a tile of 128 frames into registers (16 independent coalesced loads per thread, issued
+// while the previous tile is being consumed), park it in shared memory, and warp 0 then performs
+// the ordered float32 additions from shared memory.
+constexpr int kMeanCols = 32;
+constexpr int kMeanRows = 128;
+constexpr int kMeanThreads = 256;
+constexpr int kMeanPerThread = kMeanRows / (kMeanThreads / 32);   // 16 rows per thread per tile
 
-__global__ void __launch_bounds__(128) mean_positions_kernel(const float* __restrict__ pos, int64_t n_t,
-                                                             int64_t n_cols, float* __restrict__ mean) {
-  int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= n_cols) return;
+__global__ void __launch_bounds__(kMeanThreads) mean_positions_kernel(const float* __restrict__ pos, int64_t n_t,
+                                                                      int64_t n_cols, float* __restrict__ mean) {
+  __shared__ float tile[2][kMeanRows][kMeanCols];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t col = (int64_t)blockIdx.x * kMeanCols + lane;
+  const bool col_ok = col < n_cols;
   const float* p = pos + col;
+  const int64_t n_tiles = (n_t + kMeanRows - 1) / kMeanRows;
+
+  float v[kMeanPerThread];
+  auto fetch = [&](int64_t tile_idx) {
+    const int64_t t0 = tile_idx * kMeanRows + warp;
+#pragma unroll
+    for (int i = 0; i < kMeanPerThread; ++i) {
+      const int64_t t = t0 + (int64_t)i * (kMeanThreads / 32);
+      v[i] = (col_ok && t < n_t) ? __ldg(p + t * n_cols) : 0.0f;
+    }
+  };
+
   float acc = 0.0f;
-  int64_t t = 0;
-  for (; t + kMeanBatch <= n_t; t += kMeanBatch) {
-    float v[kMeanBatch];
+  fetch(0);
+  for (int64_t it = 0; it < n_tiles; ++it) {
+    const int buf = (int)(it & 1);
 #pragma unroll
-    for (int i = 0; i < kMeanBatch; ++i) v[i] = __ldg(p + (t + i) * n_cols);
-#pragma unroll
-    for (int i = 0; i < kMeanBatch; ++i) acc = __fadd_rn(acc, v[i]);
+    for (int i = 0; i < kMeanPerThread; ++i) tile[buf][warp + i * (kMeanThreads / 32)][lane] = v[i];
+    __syncthreads();
+    if (it + 1 < n_tiles) fetch(it + 1);              // in flight while warp 0 consumes this tile
+    if (warp == 0) {
+      const int64_t rows = (n_t - it * kMeanRows) < kMeanRows ? (n_t - it * kMeanRows) : kMeanRows;
+      if (rows == kMeanRows) {
+#pragma unroll 16
+        for (int r = 0; r < kMeanRows; ++r) acc = __fadd_rn(acc, tile[buf][r][lane]);
+      } else {
+        for (int r = 0; r < (int)rows; ++r) acc = __fadd_rn(acc, tile[buf][r][lane]);
+      }
+    }
+    // the store into tile[buf] two iterations from now is ordered after this read by the
+    // __syncthreads of the next iteration
   }
-  for (; t < n_t; ++t) acc = __fadd_rn(acc, __ldg(p + t * n_cols));
-  mean[col] = __fdiv_rn(acc, (float)n_t);
+  if (warp == 0 && col_ok) mean[col] = __fdiv_rn(acc, (float)n_t);
 }
 
 int launch_mean_positions(const float* pos, int64_t n_t, int64_t n_a, float* mean, cudaStream_t s) {
   int64_t n_cols = n_a * 3;
   if (n_cols == 0) return PSA_OK;
-  int64_t blocks = (n_cols + 127) / 128;
-  mean_positions_kernel<<<(unsigned)blocks, 128, 0, s>>>(pos, n_t, n_cols, mean);
+  int64_t blocks = (n_cols + kMeanCols - 1) / kMeanCols;
+  mean_positions_kernel<<<(unsigned)blocks, kMeanThreads, 0, s>>>(pos, n_t, n_cols, mean);
   return launch_status("mean_positions_kernel");
 }
 

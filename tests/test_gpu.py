@@ -157,7 +157,7 @@ def test_project_two_pass_accumulation(eng):
 
 
 # ------------------------------------------------------------------ FFT + assembly
-@pytest.mark.parametrize("n_t", [16, 32, 64, 1024, 2048, 16384, 32768, 65536])
+@pytest.mark.parametrize("n_t", [32, 64, 128, 1024, 2048, 8192, 16384, 32768, 65536])
 def test_fft_coherent(eng, n_t):
     rng = np.random.default_rng(n_t)
     n_k, n_k_total, k_off = 3, 5, 1
@@ -420,3 +420,16 @@ def test_full_size_config1_properties():
     s1 = calc.calculate(mags[:16], kv[:16], basis_atom_types=[1]).sed.astype(np.complex128)
     s2 = calc.calculate(mags[:16], kv[:16], basis_atom_types=[2]).sed.astype(np.complex128)
     assert np.abs(s1 + s2 - res.sed[:, :16, :]).max() < 1e-6 * np.abs(res.sed[:, :16, :]).max()
+
+
+# ------------------------------------------------------------------ multi-GPU (needs >= 2 visible devices)
+def test_k_sharded_two_gpus_equals_single_gpu():
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = Path(__file__).resolve().parent / "multigpu_check.py"
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "MULTIGPU_CHECK world=2 results=[True, True, True]" in out.stdout
