@@ -42,6 +42,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner there) must not
+# pollute it: keep a private handle on the real stdout and point fd 1 at stderr for everyone else.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 # ------------------------------------------------------------------------------------------------ workload
 def build_jobs(cfg, calc, k_mult=1):
     """[(k_mags, k_vecs, kwargs, chiral_pair|None)] for one step of the config; ``k_mult`` densifies
@@ -180,7 +191,7 @@ def run_reference(args, cfg):
             "cpu_baseline": {"value": units_per_s, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": units_per_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ roofline
@@ -392,7 +403,7 @@ def main():
             "roofline": roof, "rooflines": rooflines, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -73,20 +73,26 @@ int psa_project(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8
                 const int32_t* expo, int64_t n_t, int64_t n_sel, int64_t pitch, float* P, int64_t ldp,
                 int impl, void* stream);
 
-/* Twiddle table w[j] = exp(-2 pi i j / n), j < n, correctly rounded float32 pairs. */
-int psa_twiddles(int64_t n, float* tw, void* stream);
+/* FFT plan for n_t frames: twiddles, plus (when n_t is not a power of two) the Bluestein chirp and
+ * its spectrum.  The caller owns the buffer: allocate psa_fft_plan_bytes(n_t) device bytes (-1 = n_t not
+ * supported: 2 <= n_t <= 2^19), fill it once with psa_fft_plan_init, reuse it for every psa_fft_sed. */
+int64_t psa_fft_plan_bytes(int64_t n_t);
+int psa_fft_plan_init(int64_t n_t, void* plan, void* stream);
+
+/* Scratch bytes psa_fft_sed needs for one call (0 for power-of-two n_t; the chirped spectra otherwise). */
+int64_t psa_fft_workspace_bytes(int64_t n_t, int64_t n_k, int64_t n_groups);
 
 /* Time FFT of every (k, pol) column of P, scaled 1/n_t, fused with the assembly epilogue.
  * Replaces np.fft.fft(axis=0)/n_t and the coherent / incoherent assembly
- * (reference: sed_calculator.py:83-84, 296-327).
+ * (reference: sed_calculator.py:83-84, 296-327).  Any n_t in [2, 2^19]: powers of two >= 32 run as one
+ * in-shared-memory transform per column, other lengths through Bluestein's chirp-z identity.
  *   P   [n_groups][2 n_k][3][ldp] float32 (group g at P + g*group_stride floats)
- *   tw  psa_twiddles(n_t)
+ *   plan, workspace: see above
  *   out coherent: complex64 [n_t][n_k_total][3], this call fills k in [k_offset, k_offset+n_k)
- *       incoherent: float32 [n_t][n_k_total]
- * n_t must be a power of two >= 32 in this version. */
+ *       incoherent: float32 [n_t][n_k_total] */
 int psa_fft_sed(const float* P, int64_t n_groups, int64_t group_stride, int64_t n_k, int64_t n_t,
-                int64_t ldp, const float* tw, int mode, void* out, int64_t n_k_total, int64_t k_offset,
-                void* stream);
+                int64_t ldp, const void* plan, void* workspace, int64_t workspace_bytes, int mode, void* out,
+                int64_t n_k_total, int64_t k_offset, void* stream);
 
 /* Chiral phase of two complex components (reference: sed_calculator.py:338-371).
  *   z1, z2 complex64 with element strides stride1/stride2 (in complex elements), n elements

@@ -37,9 +37,11 @@ _SIGNATURES = {
                                  c_void_p, c_void_p]),
     "psa_project": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                             c_void_p, c_int64, c_int, c_void_p]),
-    "psa_twiddles": (c_int, [c_int64, c_void_p, c_void_p]),
-    "psa_fft_sed": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int,
-                            c_void_p, c_int64, c_int64, c_void_p]),
+    "psa_fft_plan_bytes": (c_int64, [c_int64]),
+    "psa_fft_plan_init": (c_int, [c_int64, c_void_p, c_void_p]),
+    "psa_fft_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
+    "psa_fft_sed": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64,
+                            c_int, c_void_p, c_int64, c_int64, c_void_p]),
     "psa_chiral_phase": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "psa_intensity": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "psa_ised_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_double, c_int, c_int64, c_int64,

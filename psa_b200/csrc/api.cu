@@ -87,19 +87,30 @@ int psa_project(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8
   return PSA_ERR_BAD_ARG;
 }
 
-int psa_twiddles(int64_t n, float* tw, void* stream) {
-  PSA_REQUIRE(n > 0 && tw, "psa_twiddles: bad arguments");
-  return launch_twiddles(n, reinterpret_cast<float2*>(tw), as_stream(stream));
+int64_t psa_fft_plan_bytes(int64_t n_t) {
+  int64_t bytes = 0;
+  return fft_plan_bytes(n_t, &bytes) == PSA_OK ? bytes : -1;
+}
+
+int64_t psa_fft_workspace_bytes(int64_t n_t, int64_t n_k, int64_t n_groups) {
+  int64_t bytes = 0;
+  return fft_workspace_bytes(n_t, n_k, n_groups, &bytes) == PSA_OK ? bytes : -1;
+}
+
+int psa_fft_plan_init(int64_t n_t, void* plan, void* stream) {
+  PSA_REQUIRE(plan != nullptr, "psa_fft_plan_init: null plan buffer");
+  return launch_fft_plan(n_t, reinterpret_cast<float2*>(plan), as_stream(stream));
 }
 
 int psa_fft_sed(const float* P, int64_t n_groups, int64_t group_stride, int64_t n_k, int64_t n_t, int64_t ldp,
-                const float* tw, int mode, void* out, int64_t n_k_total, int64_t k_offset, void* stream) {
-  PSA_REQUIRE(P && tw && out, "psa_fft_sed: null pointer");
+                const void* plan, void* workspace, int64_t workspace_bytes, int mode, void* out, int64_t n_k_total,
+                int64_t k_offset, void* stream) {
+  PSA_REQUIRE(P && plan && out, "psa_fft_sed: null pointer");
   PSA_REQUIRE(n_groups >= 1 && n_k > 0 && n_t > 0 && ldp >= n_t, "psa_fft_sed: bad extents");
   PSA_REQUIRE(k_offset >= 0 && k_offset + n_k <= n_k_total, "psa_fft_sed: k range outside the result");
   PSA_REQUIRE(mode == PSA_MODE_INCOHERENT || n_groups == 1, "psa_fft_sed: coherent mode takes one group");
-  return launch_fft(P, n_groups, group_stride, n_k, n_t, ldp, reinterpret_cast<const float2*>(tw), mode, out,
-                    n_k_total, k_offset, as_stream(stream));
+  return launch_fft(P, n_groups, group_stride, n_k, n_t, ldp, reinterpret_cast<const float2*>(plan), workspace,
+                    workspace_bytes, mode, out, n_k_total, k_offset, as_stream(stream));
 }
 
 int psa_chiral_phase(const float* z1, const float* z2, int64_t n, int64_t stride1, int64_t stride2, int opt,

@@ -1,46 +1,48 @@
 // Time-axis FFT of the projected columns, fused with the 1/n_t scale and the SED assembly.
 //
 // One CTA transforms one column (k, pol [, group]) entirely in shared memory and writes the spectrum
-// straight into the result layout, so spectra never round-trip through HBM:
+// straight into the result layout:
 //   coherent   : complex64 out[f][k][pol]                   (reference: sed_calculator.py:296-311)
 //   incoherent : float32  out[f][k] = sum_g sum_pol |S|^2    (reference: sed_calculator.py:313-327)
 //
-// Transform structure (forward, decimation in frequency, in place, m = 2^s points, 32 <= m <= 16384):
+// Power-of-two core (forward, decimation in frequency, in place, m = 2^s points, 32 <= m <= 16384):
 //   * shared-memory passes: one radix-2 pass if s-5 is odd, then radix-4 passes down to blocks of 32.
 //     Every butterfly leg is >= 32 elements away from the next, so a warp always touches 32
 //     consecutive elements: conflict-free.
 //   * final stage: each thread pulls one contiguous 32-point block into registers, finishes it with
-//     radix 4 x 4 x 2 and stores the 32 results directly to global memory (digit-reversed frequency
-//     index).  The array is padded by one element per 32 (index p lives at p + p/32), which makes the
-//     per-thread contiguous block reads conflict-free as well.
-// Columns longer than 16384 points do not fit one CTA's shared memory: they are split by a radix-R
-// decimation-in-frequency step applied while loading, giving R independent sub-transforms that
-// produce the frequencies f = R f' + r.
-// Twiddles come from a correctly rounded float32 table (computed in float64), like pocketfft's.
+//     radix 4 x 4 x 2 and hands the 32 results (digit-reversed frequency index) to a sink.  The array
+//     is padded by one element per 32 (index p lives at p + p/32), which makes the per-thread
+//     contiguous block reads conflict-free as well.
+//   * transforms longer than 16384 points do not fit one CTA's shared memory: they are split by a
+//     radix-R decimation-in-frequency step applied while loading, giving R independent
+//     sub-transforms that produce the frequencies f = R f' + r.
+//   * twiddles come from a correctly rounded float32 table (computed in float64), like pocketfft's.
+//
+// Frame counts that are not a power of two (the reference accepts any n_t through pocketfft) use
+// Bluestein's chirp-z identity on top of the same core: with b_t = exp(i pi t^2 / n),
+//   X_f = conj(b_f) * sum_t (x_t conj(b_t)) b_{f-t},
+// i.e. one forward transform of length M >= 2n-1 (M = 2^s), a point-wise product with the
+// precomputed spectrum of b, and one inverse transform; the chirped spectrum of each column makes
+// one round trip through a scratch buffer.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace psa {
 
 constexpr int kFftThreads = 512;
-constexpr int64_t kMaxSmemPoints = 16384;
-constexpr int kBlk = 32;   // points finished in registers per thread
+constexpr int64_t kMaxSmemPoints = 16384;   // complex64 points that fit one CTA (128 KiB + padding)
+constexpr int64_t kMaxTransform = (int64_t)1 << 20;
+constexpr int kBlk = 32;                    // points finished in registers per thread
 
-__global__ void twiddle_kernel(int64_t n, float2* __restrict__ tw) {
-  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  double s, c;
-  sincospi(2.0 * (double)j / (double)n, &s, &c);
-  tw[j] = make_float2((float)c, (float)(-s));
-}
-
-int launch_twiddles(int64_t n, float2* tw, cudaStream_t s) {
-  if (n <= 0) return PSA_OK;
-  twiddle_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, tw);
-  return launch_status("twiddle_kernel");
-}
-
+// ---------------------------------------------------------------------------------------------
+// complex helpers
+// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {   // a * conj(b)
+  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -53,6 +55,9 @@ __device__ __forceinline__ void bfly4(float2& a0, float2& a1, float2& a2, float2
   a0 = cadd(t0, t2); a1 = cadd(t1, t3); a2 = csub(t0, t2); a3 = csub(t1, t3);
 }
 
+// ---------------------------------------------------------------------------------------------
+// the power-of-two core
+// ---------------------------------------------------------------------------------------------
 // Shared-memory passes: reduce the m-point problem to m/32 independent contiguous 32-point blocks.
 __device__ void fft_smem_passes(float2* __restrict__ s, int m, int log2m, const float2* __restrict__ tw, int tw_n) {
   int L = m;
@@ -138,131 +143,434 @@ __device__ __forceinline__ int block_base_frequency(int b, int log2m) {
   return f;
 }
 
-// Load one column into shared memory, applying the radix-R split for sub-transform r (R == 1: plain copy).
-__device__ void load_column(float2* __restrict__ s, const float* __restrict__ re, const float* __restrict__ im,
-                            int m, int R, int r, const float2* __restrict__ tw) {
-  if (R == 1) {
-#pragma unroll 8
-    for (int t = threadIdx.x; t < m; t += blockDim.x) s[phys(t)] = make_float2(__ldg(re + t), __ldg(im + t));
+// Geometry of one launch: transform length n_fft = m * R, twiddle table of length n_fft.
+struct FftGeom {
+  int m, log2m, R, n_fft;
+  const float2* tw;
+};
+
+// Fill shared memory with sub-sequence r of the radix-R split of fetch(0..n_fft) (R == 1: plain copy).
+template <class Fetch>
+__device__ void load_column(float2* __restrict__ s, const Fetch& fetch, const FftGeom& g, int r) {
+  if (g.R == 1) {
+#pragma unroll 4
+    for (int t = threadIdx.x; t < g.m; t += blockDim.x) s[phys(t)] = fetch(t);
     return;
   }
-  for (int t = threadIdx.x; t < m; t += blockDim.x) {
+  for (int t = threadIdx.x; t < g.m; t += blockDim.x) {
     float2 acc = make_float2(0.f, 0.f);
-    for (int j = 0; j < R; ++j) {
-      float2 x = make_float2(__ldg(re + t + (int64_t)j * m), __ldg(im + t + (int64_t)j * m));
-      int wi = (int)(((int64_t)j * r) % R) * m;           // w_R^{jr} = w_n^{(jr mod R) m}
-      acc = cadd(acc, wi ? cmul(x, __ldg(tw + wi)) : x);
+    for (int j = 0; j < g.R; ++j) {
+      float2 x = fetch(t + j * g.m);
+      int wi = ((j * r) & (g.R - 1)) * g.m;                        // w_R^{jr} = w_n^{(jr mod R) m}
+      acc = cadd(acc, wi ? cmul(x, __ldg(g.tw + wi)) : x);
     }
-    s[phys(t)] = r ? cmul(acc, __ldg(tw + (int64_t)t * r)) : acc;   // w_n^{tr}, t r < n
+    s[phys(t)] = r ? cmul(acc, __ldg(g.tw + (int64_t)t * r)) : acc;   // w_n^{tr}, t r < n
   }
 }
 
-template <int kMode>
-__global__ void __launch_bounds__(kFftThreads) fft_sed_kernel(
-    const float* __restrict__ P, int n_groups, int64_t group_stride, int n_k, int n_t, int64_t ldp,
-    const float2* __restrict__ tw, void* __restrict__ out, int64_t n_k_total, int64_t k_offset, int m, int log2m,
-    int R) {
-  extern __shared__ float2 s_data[];
-  const float inv_n = 1.0f / (float)n_t;   // n_t is a power of two: the product equals the reference's division
-  const int n_blocks = m >> 5;
-  const int fstep = m >> 5;                // frequency step between register elements with rev(e) = 1
+// Transform the column in shared memory and feed every (slot, frequency, value) to the sink.
+// slot = padded in-place position, owned by the same thread on every call with the same geometry.
+template <class Sink>
+__device__ void transform_and_emit(float2* __restrict__ s, const FftGeom& g, int r, Sink& sink) {
+  fft_smem_passes(s, g.m, g.log2m, g.tw, g.n_fft);
+  const int n_blocks = g.m >> 5, fstep = g.m >> 5;
+  for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) {
+    float2 x[kBlk];
+#pragma unroll
+    for (int e = 0; e < kBlk; ++e) x[e] = s[b * (kBlk + 1) + e];
+    fft32_registers(x, g.tw, g.n_fft);
+    const int f0 = block_base_frequency(b, g.log2m);
+#pragma unroll
+    for (int e = 0; e < kBlk; ++e) {
+      const int rev = (e >> 3) + 4 * ((e >> 1) & 3) + 16 * (e & 1);
+      sink(b * (kBlk + 1) + e, (f0 + fstep * rev) * g.R + r, x[e]);
+    }
+  }
+}
 
-  if (kMode == PSA_MODE_COHERENT) {
-    // block -> (k, pol, r)
-    const int r = blockIdx.x % R;
-    const int pol = (blockIdx.x / R) % 3;
-    const int k = blockIdx.x / (3 * R);
-    const float* re = P + ((int64_t)(2 * k) * 3 + pol) * ldp;
-    const float* im = P + ((int64_t)(2 * k + 1) * 3 + pol) * ldp;
-    load_column(s_data, re, im, m, R, r, tw);
+// ---------------------------------------------------------------------------------------------
+// fetchers
+// ---------------------------------------------------------------------------------------------
+struct FetchPlanar {            // rows of P: Re and Im as separate float rows
+  const float* re;
+  const float* im;
+  __device__ float2 operator()(int t) const { return make_float2(__ldg(re + t), __ldg(im + t)); }
+};
+struct FetchChirped {           // x_t * conj(b_t) for t < n, zero padding up to the transform length
+  const float* re;
+  const float* im;
+  const float2* chirp;
+  int n;
+  __device__ float2 operator()(int t) const {
+    if (t >= n) return make_float2(0.f, 0.f);
+    return cmul_conj(make_float2(__ldg(re + t), __ldg(im + t)), __ldg(chirp + t));
+  }
+};
+struct FetchConj {              // conj of an interleaved complex column (inverse transform by conjugation)
+  const float2* src;
+  __device__ float2 operator()(int t) const {
+    float2 v = __ldg(src + t);
+    return make_float2(v.x, -v.y);
+  }
+};
+struct FetchComplex {
+  const float2* src;
+  __device__ float2 operator()(int t) const { return __ldg(src + t); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// sinks
+// ---------------------------------------------------------------------------------------------
+// value -> S = value * scale (power-of-two path) or the Bluestein unchirp; then the SED assembly.
+struct Unchirp {                // Bluestein: X_f = conj(b_f) * conj(y_f) / M, then / n   (f < n only)
+  const float2* chirp;
+  int n;
+  float inv_m, n_f;
+  __device__ bool operator()(int f, float2 y, float2& out) const {
+    if (f >= n) return false;
+    float2 conv = make_float2(y.x * inv_m, -y.y * inv_m);
+    float2 X = cmul_conj(conv, __ldg(chirp + f));
+    out = make_float2(X.x / n_f, X.y / n_f);            // divide by n_t like the reference
+    return true;
+  }
+};
+struct ScaleOnly {              // power of two: multiply by the exact reciprocal 1 / n_t
+  float inv_n;
+  __device__ bool operator()(int, float2 y, float2& out) const {
+    out = make_float2(y.x * inv_n, y.y * inv_n);
+    return true;
+  }
+};
+
+template <class Post>
+struct SinkCoherent {
+  float2* o;                    // already offset to (k, pol)
+  int64_t fstride;
+  Post post;
+  __device__ void operator()(int, int f, float2 v) const {
+    float2 S;
+    if (post(f, v, S)) o[(int64_t)f * fstride] = S;
+  }
+};
+template <class Post>
+struct SinkAccumulate {         // s_acc[slot] += |S|^2; the slot is private to the calling thread
+  float* s_acc;
+  Post post;
+  __device__ void operator()(int slot, int f, float2 v) const {
+    float2 S;
+    if (post(f, v, S)) s_acc[slot] += S.x * S.x + S.y * S.y;
+  }
+};
+struct SinkFlush {              // write the accumulated intensities of one k column
+  const float* s_acc;
+  float* o;                     // already offset to k
+  int64_t fstride;
+  int n_valid;
+  __device__ void operator()(int slot, int f, float2) const {
+    if (f < n_valid) o[(int64_t)f * fstride] = s_acc[slot];
+  }
+};
+struct SinkTimesSpectrum {      // natural-order store of value * bhat[f] (Bluestein forward leg)
+  float2* dst;
+  const float2* bhat;           // nullptr: plain store
+  __device__ void operator()(int, int f, float2 v) const { dst[f] = bhat ? cmul(v, __ldg(bhat + f)) : v; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+struct SedArgs {
+  const float* P;
+  int n_groups;
+  int64_t group_stride, ldp;
+  int n_t;
+  void* out;
+  int64_t n_k_total, k_offset;
+};
+
+__device__ __forceinline__ void column_rows(const SedArgs& a, int g, int k, int pol, const float*& re, const float*& im) {
+  const float* base = a.P + (int64_t)g * a.group_stride;
+  re = base + ((int64_t)(2 * k) * 3 + pol) * a.ldp;
+  im = base + ((int64_t)(2 * k + 1) * 3 + pol) * a.ldp;
+}
+
+// Power-of-two n_t: P -> result in one kernel.
+template <int kMode>
+__global__ void __launch_bounds__(kFftThreads) fft_sed_kernel(SedArgs a, FftGeom g) {
+  extern __shared__ float2 s_data[];
+  const ScaleOnly post{1.0f / (float)a.n_t};
+  const int r = blockIdx.x % g.R;
+  if (kMode == PSA_MODE_COHERENT) {          // block -> (k, pol, r)
+    const int pol = (blockIdx.x / g.R) % 3, k = blockIdx.x / (3 * g.R);
+    FetchPlanar fetch;
+    column_rows(a, 0, k, pol, fetch.re, fetch.im);
+    load_column(s_data, fetch, g, r);
     __syncthreads();
-    fft_smem_passes(s_data, m, log2m, tw, n_t);
-    float2* o = reinterpret_cast<float2*>(out) + (k_offset + k) * 3 + pol;
-    const int64_t fstride = n_k_total * 3;
-    for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) {
-      float2 x[kBlk];
-#pragma unroll
-      for (int e = 0; e < kBlk; ++e) x[e] = s_data[b * (kBlk + 1) + e];
-      fft32_registers(x, tw, n_t);
-      const int f0 = block_base_frequency(b, log2m);
-#pragma unroll
-      for (int e = 0; e < kBlk; ++e) {
-        const int rev = (e >> 3) + 4 * ((e >> 1) & 3) + 16 * (e & 1);
-        const int64_t f = (int64_t)(f0 + fstep * rev) * R + r;
-        o[f * fstride] = make_float2(x[e].x * inv_n, x[e].y * inv_n);
-      }
-    }
-  } else {
-    // block -> (k, r); loop over groups and polarisations, accumulate |S|^2 per (padded) position
-    float* s_acc = reinterpret_cast<float*>(s_data + m + (m >> 5));
-    const int r = blockIdx.x % R;
-    const int k = blockIdx.x / R;
-    for (int b = threadIdx.x; b < n_blocks; b += blockDim.x)
-#pragma unroll
-      for (int e = 0; e < kBlk; ++e) s_acc[b * (kBlk + 1) + e] = 0.f;
-    for (int g = 0; g < n_groups; ++g) {
+    SinkCoherent<ScaleOnly> sink{reinterpret_cast<float2*>(a.out) + (a.k_offset + k) * 3 + pol, a.n_k_total * 3, post};
+    transform_and_emit(s_data, g, r, sink);
+  } else {                                   // block -> (k, r); loop over groups and polarisations
+    const int k = blockIdx.x / g.R;
+    const int padded = g.m + (g.m >> 5);
+    float* s_acc = reinterpret_cast<float*>(s_data + padded);
+    for (int i = threadIdx.x; i < padded; i += blockDim.x) s_acc[i] = 0.f;
+    SinkAccumulate<ScaleOnly> acc{s_acc, post};
+    for (int grp = 0; grp < a.n_groups; ++grp)
       for (int pol = 0; pol < 3; ++pol) {
-        const float* base = P + (int64_t)g * group_stride;
-        const float* re = base + ((int64_t)(2 * k) * 3 + pol) * ldp;
-        const float* im = base + ((int64_t)(2 * k + 1) * 3 + pol) * ldp;
+        FetchPlanar fetch;
+        column_rows(a, grp, k, pol, fetch.re, fetch.im);
         __syncthreads();
-        load_column(s_data, re, im, m, R, r, tw);
+        load_column(s_data, fetch, g, r);
         __syncthreads();
-        fft_smem_passes(s_data, m, log2m, tw, n_t);
-        for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) {
-          float2 x[kBlk];
-#pragma unroll
-          for (int e = 0; e < kBlk; ++e) x[e] = s_data[b * (kBlk + 1) + e];
-          fft32_registers(x, tw, n_t);
-#pragma unroll
-          for (int e = 0; e < kBlk; ++e) {
-            const float vr = x[e].x * inv_n, vi = x[e].y * inv_n;
-            s_acc[b * (kBlk + 1) + e] += vr * vr + vi * vi;     // same thread owns this slot every time
-          }
-        }
+        transform_and_emit(s_data, g, r, acc);
       }
-    }
-    float* o = reinterpret_cast<float*>(out) + k_offset + k;
+    // every slot was accumulated and is flushed by the same thread: no barrier needed
+    SinkFlush flush{s_acc, reinterpret_cast<float*>(a.out) + a.k_offset + k, a.n_k_total, g.n_fft};
+    const int n_blocks = g.m >> 5, fstep = g.m >> 5;
     for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) {
-      const int f0 = block_base_frequency(b, log2m);
+      const int f0 = block_base_frequency(b, g.log2m);
 #pragma unroll
       for (int e = 0; e < kBlk; ++e) {
         const int rev = (e >> 3) + 4 * ((e >> 1) & 3) + 16 * (e & 1);
-        const int64_t f = (int64_t)(f0 + fstep * rev) * R + r;
-        o[f * n_k_total] = s_acc[b * (kBlk + 1) + e];
+        flush(b * (kBlk + 1) + e, (f0 + fstep * rev) * g.R + r, make_float2(0.f, 0.f));
       }
     }
   }
+}
+
+// Bluestein leg 1: column -> chirp, zero-pad, forward transform, times the chirp spectrum -> scratch.
+// block -> (column, r), column = (group, k, pol) flattened.
+__global__ void __launch_bounds__(kFftThreads) bluestein_forward_kernel(SedArgs a, FftGeom g, int n_k,
+                                                                        const float2* __restrict__ chirp,
+                                                                        const float2* __restrict__ bhat,
+                                                                        float2* __restrict__ scratch) {
+  extern __shared__ float2 s_data[];
+  const int r = blockIdx.x % g.R;
+  const int col = blockIdx.x / g.R;
+  const int pol = col % 3, k = (col / 3) % n_k, grp = col / (3 * n_k);
+  FetchChirped fetch;
+  column_rows(a, grp, k, pol, fetch.re, fetch.im);
+  fetch.chirp = chirp;
+  fetch.n = a.n_t;
+  load_column(s_data, fetch, g, r);
+  __syncthreads();
+  SinkTimesSpectrum sink{scratch + (int64_t)col * g.n_fft, bhat};
+  transform_and_emit(s_data, g, r, sink);
+}
+
+// Bluestein leg 2: scratch -> inverse transform (by conjugation), unchirp, / n_t, SED assembly.
+template <int kMode>
+__global__ void __launch_bounds__(kFftThreads) bluestein_inverse_kernel(SedArgs a, FftGeom g, int n_k,
+                                                                        const float2* __restrict__ chirp,
+                                                                        const float2* __restrict__ scratch) {
+  extern __shared__ float2 s_data[];
+  const Unchirp post{chirp, a.n_t, 1.0f / (float)g.n_fft, (float)a.n_t};
+  const int r = blockIdx.x % g.R;
+  if (kMode == PSA_MODE_COHERENT) {
+    const int col = blockIdx.x / g.R;          // (k, pol), single group
+    const int pol = col % 3, k = col / 3;
+    FetchConj fetch{scratch + (int64_t)col * g.n_fft};
+    load_column(s_data, fetch, g, r);
+    __syncthreads();
+    SinkCoherent<Unchirp> sink{reinterpret_cast<float2*>(a.out) + (a.k_offset + k) * 3 + pol, a.n_k_total * 3, post};
+    transform_and_emit(s_data, g, r, sink);
+  } else {
+    const int k = blockIdx.x / g.R;
+    const int padded = g.m + (g.m >> 5);
+    float* s_acc = reinterpret_cast<float*>(s_data + padded);
+    for (int i = threadIdx.x; i < padded; i += blockDim.x) s_acc[i] = 0.f;
+    SinkAccumulate<Unchirp> acc{s_acc, post};
+    for (int grp = 0; grp < a.n_groups; ++grp)
+      for (int pol = 0; pol < 3; ++pol) {
+        const int col = (grp * n_k + k) * 3 + pol;
+        FetchConj fetch{scratch + (int64_t)col * g.n_fft};
+        __syncthreads();
+        load_column(s_data, fetch, g, r);
+        __syncthreads();
+        transform_and_emit(s_data, g, r, acc);
+      }
+    SinkFlush flush{s_acc, reinterpret_cast<float*>(a.out) + a.k_offset + k, a.n_k_total, a.n_t};
+    const int n_blocks = g.m >> 5, fstep = g.m >> 5;
+    for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) {
+      const int f0 = block_base_frequency(b, g.log2m);
+#pragma unroll
+      for (int e = 0; e < kBlk; ++e) {
+        const int rev = (e >> 3) + 4 * ((e >> 1) & 3) + 16 * (e & 1);
+        flush(b * (kBlk + 1) + e, (f0 + fstep * rev) * g.R + r, make_float2(0.f, 0.f));
+      }
+    }
+  }
+}
+
+// plain complex-to-complex forward transform of one column, natural order (used once per plan)
+__global__ void __launch_bounds__(kFftThreads) fft_c2c_kernel(const float2* __restrict__ src, float2* __restrict__ dst,
+                                                              FftGeom g) {
+  extern __shared__ float2 s_data[];
+  const int r = blockIdx.x % g.R;
+  FetchComplex fetch{src};
+  load_column(s_data, fetch, g, r);
+  __syncthreads();
+  SinkTimesSpectrum sink{dst, nullptr};
+  transform_and_emit(s_data, g, r, sink);
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan: twiddles (+ chirp and its spectrum for non-power-of-two lengths), one caller-owned buffer
+//   power of two : [ tw (n_t) ]
+//   otherwise    : [ tw (M) | chirp (n_t) | bhat (M) | work (M) ]      all float2
+// ---------------------------------------------------------------------------------------------
+__global__ void twiddle_kernel(int64_t n, float2* __restrict__ tw) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double s, c;
+  sincospi(2.0 * (double)j / (double)n, &s, &c);
+  tw[j] = make_float2((float)c, (float)(-s));
+}
+
+// chirp[t] = exp(+i pi t^2 / n) with t^2 reduced mod 2n in integers; padded[] = the circular kernel of length M
+__global__ void chirp_kernel(int64_t n, int64_t M, float2* __restrict__ chirp, float2* __restrict__ padded) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M) return;
+  float2 val = make_float2(0.f, 0.f);
+  int64_t src = t < n ? t : (M - t < n ? M - t : -1);        // b_{-t} = b_t wraps to M - t
+  if (src >= 0) {
+    int64_t q = (src * src) % (2 * n);
+    double s, c;
+    sincospi((double)q / (double)n, &s, &c);
+    val = make_float2((float)c, (float)s);
+    if (t < n) chirp[t] = val;
+  }
+  padded[t] = val;
+}
+
+static bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+
+static int64_t bluestein_length(int64_t n) {
+  int64_t m = 32;
+  while (m < 2 * n - 1) m <<= 1;
+  return m;
+}
+
+static FftGeom make_geom(int64_t n_fft, const float2* tw) {
+  static const int64_t max_points = []() -> int64_t {     // tuning knob, see profiles/
+    const char* env = getenv("PSA_FFT_MAX_POINTS");
+    int64_t v = env ? atoll(env) : kMaxSmemPoints;
+    if (v < 64 || v > kMaxSmemPoints || (v & (v - 1))) v = kMaxSmemPoints;
+    return v;
+  }();
+  FftGeom g;
+  int64_t m = n_fft;
+  int R = 1;
+  while (m > max_points) { m >>= 1; R <<= 1; }
+  g.m = (int)m;
+  g.R = R;
+  g.n_fft = (int)n_fft;
+  g.log2m = 0;
+  while ((1 << g.log2m) < m) ++g.log2m;
+  g.tw = tw;
+  return g;
+}
+
+static size_t smem_bytes(const FftGeom& g, bool with_acc) {
+  const size_t padded = (size_t)(g.m + (g.m >> 5));
+  return padded * sizeof(float2) + (with_acc ? padded * sizeof(float) : 0);
+}
+
+template <class K>
+static int allow_smem(K kernel, size_t bytes) {
+  PSA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return PSA_OK;
+}
+
+int fft_plan_bytes(int64_t n_t, int64_t* bytes) {
+  if (n_t < 2 || n_t > kMaxTransform / 2) {
+    set_error("psa_fft: n_t=%lld is outside the supported range [2, %lld]", (long long)n_t, (long long)(kMaxTransform / 2));
+    return PSA_ERR_UNSUPPORTED;
+  }
+  if (is_pow2(n_t) && n_t >= kBlk) {
+    *bytes = n_t * (int64_t)sizeof(float2);
+  } else {
+    const int64_t M = bluestein_length(n_t);
+    *bytes = (3 * M + round_up(n_t, 2)) * (int64_t)sizeof(float2);
+  }
+  return PSA_OK;
+}
+
+int launch_fft_plan(int64_t n_t, float2* plan, cudaStream_t s) {
+  int64_t bytes = 0;
+  int st = fft_plan_bytes(n_t, &bytes);
+  if (st != PSA_OK) return st;
+  if (is_pow2(n_t) && n_t >= kBlk) {
+    twiddle_kernel<<<(unsigned)((n_t + 255) / 256), 256, 0, s>>>(n_t, plan);
+    return launch_status("twiddle_kernel");
+  }
+  const int64_t M = bluestein_length(n_t);
+  float2* tw = plan;
+  float2* chirp = tw + M;
+  float2* bhat = chirp + round_up(n_t, 2);
+  float2* work = bhat + M;
+  twiddle_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(M, tw);
+  chirp_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(n_t, M, chirp, work);
+  FftGeom g = make_geom(M, tw);
+  st = allow_smem(fft_c2c_kernel, smem_bytes(g, false));
+  if (st != PSA_OK) return st;
+  fft_c2c_kernel<<<(unsigned)g.R, kFftThreads, smem_bytes(g, false), s>>>(work, bhat, g);
+  return launch_status("fft plan kernels");
+}
+
+int fft_workspace_bytes(int64_t n_t, int64_t n_k, int64_t n_groups, int64_t* bytes) {
+  int64_t plan = 0;
+  int st = fft_plan_bytes(n_t, &plan);
+  if (st != PSA_OK) return st;
+  *bytes = (is_pow2(n_t) && n_t >= kBlk) ? 0 : n_groups * n_k * 3 * bluestein_length(n_t) * (int64_t)sizeof(float2);
+  return PSA_OK;
 }
 
 int launch_fft(const float* P, int64_t n_groups, int64_t group_stride, int64_t n_k, int64_t n_t, int64_t ldp,
-               const float2* tw, int mode, void* out, int64_t n_k_total, int64_t k_offset, cudaStream_t s) {
+               const float2* plan, void* workspace, int64_t workspace_bytes, int mode, void* out, int64_t n_k_total,
+               int64_t k_offset, cudaStream_t s) {
   if (n_k == 0 || n_t == 0) return PSA_OK;
   PSA_REQUIRE(mode == PSA_MODE_COHERENT || mode == PSA_MODE_INCOHERENT, "psa_fft_sed: unknown mode %d", mode);
-  if ((n_t & (n_t - 1)) != 0 || n_t < kBlk || n_t > (int64_t)kMaxSmemPoints * 64) {
-    set_error("psa_fft_sed: n_t=%lld is not a supported length (power of two, 32 <= n_t <= 2^20)", (long long)n_t);
-    return PSA_ERR_UNSUPPORTED;
-  }
-  int R = 1;
-  int64_t m = n_t;
-  while (m > kMaxSmemPoints) { m >>= 1; R <<= 1; }
-  int log2m = 0;
-  while ((1 << log2m) < m) ++log2m;
+  int64_t need = 0;
+  int st = fft_workspace_bytes(n_t, n_k, n_groups, &need);
+  if (st != PSA_OK) return st;
+  PSA_REQUIRE(need == 0 || (workspace != nullptr && workspace_bytes >= need),
+              "psa_fft_sed: workspace of %lld bytes required for n_t=%lld (got %lld)", (long long)need,
+              (long long)n_t, (long long)workspace_bytes);
+  SedArgs a{P, (int)n_groups, group_stride, ldp, (int)n_t, out, n_k_total, k_offset};
+  const bool coherent = mode == PSA_MODE_COHERENT;
 
-  const size_t padded = (size_t)(m + (m >> 5));
-  size_t smem = padded * sizeof(float2) + (mode == PSA_MODE_INCOHERENT ? padded * sizeof(float) : 0);
-  if (mode == PSA_MODE_COHERENT) {
-    PSA_CUDA(cudaFuncSetAttribute(fft_sed_kernel<PSA_MODE_COHERENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    unsigned blocks = (unsigned)(n_k * 3 * R);
-    fft_sed_kernel<PSA_MODE_COHERENT><<<blocks, kFftThreads, smem, s>>>(P, (int)n_groups, group_stride, (int)n_k, (int)n_t,
-                                                                      ldp, tw, out, n_k_total, k_offset, (int)m, log2m, R);
-  } else {
-    PSA_CUDA(cudaFuncSetAttribute(fft_sed_kernel<PSA_MODE_INCOHERENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    unsigned blocks = (unsigned)(n_k * R);
-    fft_sed_kernel<PSA_MODE_INCOHERENT><<<blocks, kFftThreads, smem, s>>>(P, (int)n_groups, group_stride, (int)n_k, (int)n_t,
-                                                                        ldp, tw, out, n_k_total, k_offset, (int)m, log2m, R);
+  if (need == 0) {                                       // power of two: one fused kernel
+    FftGeom g = make_geom(n_t, plan);
+    const size_t smem = smem_bytes(g, !coherent);
+    if (coherent) {
+      if ((st = allow_smem(fft_sed_kernel<PSA_MODE_COHERENT>, smem)) != PSA_OK) return st;
+      fft_sed_kernel<PSA_MODE_COHERENT><<<(unsigned)(n_k * 3 * g.R), kFftThreads, smem, s>>>(a, g);
+    } else {
+      if ((st = allow_smem(fft_sed_kernel<PSA_MODE_INCOHERENT>, smem)) != PSA_OK) return st;
+      fft_sed_kernel<PSA_MODE_INCOHERENT><<<(unsigned)(n_k * g.R), kFftThreads, smem, s>>>(a, g);
+    }
+    return launch_status("fft_sed_kernel");
   }
-  return launch_status("fft_sed_kernel");
+
+  const int64_t M = bluestein_length(n_t);
+  const float2* tw = plan;
+  const float2* chirp = tw + M;
+  const float2* bhat = chirp + round_up(n_t, 2);
+  float2* scratch = reinterpret_cast<float2*>(workspace);
+  FftGeom g = make_geom(M, tw);
+  if ((st = allow_smem(bluestein_forward_kernel, smem_bytes(g, false))) != PSA_OK) return st;
+  bluestein_forward_kernel<<<(unsigned)(n_groups * n_k * 3 * g.R), kFftThreads, smem_bytes(g, false), s>>>(
+      a, g, (int)n_k, chirp, bhat, scratch);
+  if ((st = launch_status("bluestein_forward_kernel")) != PSA_OK) return st;
+  const size_t smem = smem_bytes(g, !coherent);
+  if (coherent) {
+    if ((st = allow_smem(bluestein_inverse_kernel<PSA_MODE_COHERENT>, smem)) != PSA_OK) return st;
+    bluestein_inverse_kernel<PSA_MODE_COHERENT><<<(unsigned)(n_k * 3 * g.R), kFftThreads, smem, s>>>(a, g, (int)n_k, chirp, scratch);
+  } else {
+    if ((st = allow_smem(bluestein_inverse_kernel<PSA_MODE_INCOHERENT>, smem)) != PSA_OK) return st;
+    bluestein_inverse_kernel<PSA_MODE_INCOHERENT><<<(unsigned)(n_k * g.R), kFftThreads, smem, s>>>(a, g, (int)n_k, chirp, scratch);
+  }
+  return launch_status("bluestein_inverse_kernel");
 }
 
 }  // namespace psa

@@ -9,14 +9,21 @@
 // result does not depend on tile shapes, K order or clock - it is reproducible bit for bit by
 // the integer model in tests/.
 //
-// Structure (one persistent CTA per SM, 192 threads):
-//   warp 0 lane 0 : TMA producer  - 2 bulk tensor copies per stage (A: 4x128x64 B, B: 4x128x64 B),
-//                   64-byte swizzle, 3-stage mbarrier ring
-//   warp 1 lane 0 : MMA issuer    - 20 tcgen05.mma.kind::i8 (M128 N128 K32) per stage into
+// Tile: M = 128 frames of one polarisation (TMEM lanes) x N <= 128 phase rows (TMEM columns; a row
+// is cos or sin of one k-point).  Frames are the M side because n_t is always a large multiple of
+// 128 while the number of rows is ragged: N is rounded up to 16 per tile, so a 400-row k-path costs
+// 3 x 128 + 16 columns rather than 4 x 128, the row exponent is one value per thread, and a warp's
+// store of one output row is a coalesced 128-byte line.
+//
+// Structure (one persistent CTA per SM, 320 threads):
+//   warp 0 lane 0 : TMA producer  - 2 bulk tensor copies per stage (trajectory digits 4x128x64 B,
+//                   phase digits 4x128x64 B), 64-byte swizzle, 3-stage mbarrier ring
+//   warp 1 lane 0 : MMA issuer    - 20 tcgen05.mma.kind::i8 (M128 N<=128 K32) per stage into
 //                   4 x 128 TMEM columns, tcgen05.commit releases the stage / publishes the tile
-//   warps 2..5    : epilogue      - tcgen05.ld 32x32b, int64 recombination, float32 store
+//   warps 2..9    : epilogue      - two warps per TMEM lane quarter (each takes half the columns):
+//                   tcgen05.ld 32x32b, int64 recombination, float32 store
 // TMEM is fully used by the four accumulator classes (4 x 128 columns), so the epilogue of a tile
-// is not overlapped with the next tile's MMAs; with >= 2048 atoms it is < 10 % of the tile time.
+// is not overlapped with the next tile's MMAs; the producer does keep prefetching through it.
 #include <cuda.h>
 
 #include "project_common.cuh"
@@ -24,8 +31,8 @@
 namespace psa {
 namespace tc {
 
-constexpr int BM = 128;            // rows (2 per k-point) per tile == TMEM lanes
-constexpr int BN = 128;            // frames per tile == TMEM columns per class
+constexpr int BM = 128;            // frames per tile == TMEM lanes
+constexpr int BN = 128;            // phase rows (2 per k-point) per tile == TMEM columns per class
 constexpr int BK = 64;             // atoms per stage == one 64-byte swizzle row
 constexpr int UMMA_K = 32;         // atoms per tcgen05.mma.kind::i8
 constexpr int STAGES = 3;
@@ -34,7 +41,8 @@ constexpr int OPERAND_BYTES = kSlices * SLICE_BYTES;   // 32 KiB
 constexpr int STAGE_BYTES = 2 * OPERAND_BYTES;         // 64 KiB
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -95,25 +103,29 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
-// Instruction descriptor: D = s32, A = B = s8, both K-major, M = 128, N = 128.
-constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// Instruction descriptor: D = s32, A = B = s8, both K-major, M = 128, N = n (multiple of 16).
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
 
 struct TileCoord {
-  int m_tile, pol, t_tile;
+  int r_tile, pol, t_tile, n_cols;   // n_cols: valid phase rows in this tile, rounded up to 16
 };
-__device__ __forceinline__ TileCoord decode_tile(int tile, int m_tiles, int n_tiles) {
+__device__ __forceinline__ TileCoord decode_tile(int tile, int r_tiles, int t_tiles, int rows) {
   TileCoord c;
-  c.m_tile = tile % m_tiles;          // row tiles fastest: concurrent CTAs share the same B strip
-  int n = tile / m_tiles;
-  c.pol = n / n_tiles;
-  c.t_tile = n % n_tiles;
+  c.r_tile = tile % r_tiles;          // row tiles fastest: concurrent CTAs share the same trajectory strip
+  int n = tile / r_tiles;
+  c.pol = n / t_tiles;
+  c.t_tile = n % t_tiles;
+  int left = rows - c.r_tile * BN;
+  c.n_cols = left >= BN ? BN : ((left + 15) & ~15);
   return c;
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
 project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const int32_t* __restrict__ expo, float* __restrict__ P, int rows, int n_t, int64_t ldp,
-                  int a_begin, int a_end, int accumulate, int m_tiles, int n_tiles) {
+                  int a_begin, int a_end, int accumulate, int r_tiles, int t_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -130,7 +142,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 128);
+    mbar_init(tmem_empty, 32 * EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_b) : "memory");
@@ -144,7 +156,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  const int total_tiles = m_tiles * n_tiles * 3;
+  const int total_tiles = r_tiles * t_tiles * 3;
   const int num_kb = (a_end - a_begin + BK - 1) / BK;
 
   if (warp == 0) {
@@ -152,14 +164,14 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        TileCoord tc = decode_tile(tile, m_tiles, n_tiles);
+        TileCoord tc = decode_tile(tile, r_tiles, t_tiles, rows);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           uint32_t dst = smem_u32(smem + stage * STAGE_BYTES);
           int atom0 = a_begin + kb * BK;
-          tma_load_3d(dst, &tmap_a, &full_bar[stage], atom0, tc.m_tile * BM, 0);
-          tma_load_3d(dst + OPERAND_BYTES, &tmap_b, &full_bar[stage], atom0, tc.t_tile * BN, tc.pol * kSlices);
+          tma_load_3d(dst, &tmap_b, &full_bar[stage], atom0, tc.t_tile * BM, tc.pol * kSlices);   // M side
+          tma_load_3d(dst + OPERAND_BYTES, &tmap_a, &full_bar[stage], atom0, tc.r_tile * BN, 0);    // N side
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -169,13 +181,15 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int stage = 0;
       uint32_t phase = 0, tile_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(tile, r_tiles, t_tiles, rows);
+        const uint32_t idesc = make_idesc(tc.n_cols);
         mbar_wait(tmem_empty, tile_phase ^ 1);                 // epilogue has drained the accumulators
         tc_fence_after();
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t b_base = a_base + OPERAND_BYTES;
+          const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);   // trajectory digits (M side)
+          const uint32_t b_base = a_base + OPERAND_BYTES;                 // phase digits (N side)
 #pragma unroll
           for (int ks = 0; ks < BK / UMMA_K; ++ks) {
 #pragma unroll
@@ -188,7 +202,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 const uint32_t d = tmem_base + (uint32_t)((si + sj - kMinClass) * BN);
                 // the first product issued into each class (sj == 3) overwrites, the rest accumulate
                 const uint32_t acc = (kb > 0 || ks > 0 || sj != kSlices - 1) ? 1u : 0u;
-                tc_mma_i8(d, da, db, kIdesc, acc);
+                tc_mma_i8(d, da, db, idesc, acc);
               }
             }
           }
@@ -199,47 +213,37 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         tile_phase ^= 1;
       }
     }
-  } else {                                                     // ---------------- epilogue warps 2..5
+  } else {                                                     // ---------------- epilogue warps 2..9
     const int quarter = warp & 3;                              // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;                          // which 64 columns of each class it drains
     uint32_t tile_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      TileCoord tc = decode_tile(tile, m_tiles, n_tiles);
+      const TileCoord tc = decode_tile(tile, r_tiles, t_tiles, rows);
       mbar_wait(tmem_full, tile_phase);
       tc_fence_after();
-      const int row = tc.m_tile * BM + quarter * 32 + lane;
+      const int t = tc.t_tile * BM + quarter * 32 + lane;      // this thread's frame
+      const bool t_ok = t < n_t;
+      const int e = t_ok ? __ldg(expo + (int64_t)tc.pol * n_t + t) : kExpMin;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      float* prow = P + ((int64_t)row * 3 + tc.pol) * ldp;
-      const int32_t* erow = expo + (int64_t)tc.pol * n_t;
+      const int c_end = min(tc.n_cols, half * 64 + 64);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
+      for (int c0 = half * 64; c0 < c_end; c0 += 16) {
         uint32_t r0[16], r1[16], r2[16], r3[16];
         PSA_TMEM_LD16(r0, lane_addr + 0 * BN + c0);
         PSA_TMEM_LD16(r1, lane_addr + 1 * BN + c0);
         PSA_TMEM_LD16(r2, lane_addr + 2 * BN + c0);
         PSA_TMEM_LD16(r3, lane_addr + 3 * BN + c0);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const int t0 = tc.t_tile * BN + c0;
-        if (row < rows) {
+        if (t_ok) {
+          const int row0 = tc.r_tile * BN + c0;
+          float* dst = P + ((int64_t)row0 * 3 + tc.pol) * ldp + t;
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const int t = t0 + v * 4;
-            if (t >= ldp) break;
-            float4 o;
-            float* of = reinterpret_cast<float*>(&o);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int tt = t + u;
-              const int e = tt < n_t ? __ldg(erow + tt) : kExpMin;
-              const int i = v * 4 + u;
-              of[u] = combine_classes((int32_t)r0[i], (int32_t)r1[i], (int32_t)r2[i], (int32_t)r3[i], e);
+          for (int i = 0; i < 16; ++i) {
+            if (row0 + i < rows) {
+              float v = combine_classes((int32_t)r0[i], (int32_t)r1[i], (int32_t)r2[i], (int32_t)r3[i], e);
+              float* d = dst + (int64_t)i * 3 * ldp;             // a warp writes one 128-byte line per row
+              *d = accumulate ? __fadd_rn(*d, v) : v;
             }
-            float4* dst = reinterpret_cast<float4*>(prow + t);
-            if (accumulate) {
-              float4 old = *dst;
-              o.x = __fadd_rn(old.x, o.x); o.y = __fadd_rn(old.y, o.y);
-              o.z = __fadd_rn(old.z, o.z); o.w = __fadd_rn(old.w, o.w);
-            }
-            *dst = o;
           }
         }
       }
@@ -320,16 +324,16 @@ int launch_project_tc(const int8_t* adig, int64_t rows, int64_t rows_alloc, cons
   int dev = 0, sms = 0;
   PSA_CUDA(cudaGetDevice(&dev));
   PSA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int m_tiles = (int)((rows + BM - 1) / BM);
-  const int n_tiles = (int)((n_t + BN - 1) / BN);
-  const int total = m_tiles * n_tiles * 3;
+  const int r_tiles = (int)((rows + BN - 1) / BN);
+  const int t_tiles = (int)((n_t + BM - 1) / BM);
+  const int total = r_tiles * t_tiles * 3;
   const int grid = total < sms ? total : sms;
 
   int pass = 0;
   for (int64_t a0 = 0; a0 < n_sel; a0 += kMaxAtomsPerPass, ++pass) {
     int64_t a1 = a0 + kMaxAtomsPerPass < n_sel ? a0 + kMaxAtomsPerPass : n_sel;
     project_tc_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, expo, P, (int)rows, (int)n_t, ldp, (int)a0,
-                                                        (int)a1, pass > 0, m_tiles, n_tiles);
+                                                        (int)a1, pass > 0, r_tiles, t_tiles);
     st = launch_status("project_tc_kernel");
     if (st != PSA_OK) return st;
   }

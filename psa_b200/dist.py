@@ -37,6 +37,9 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     if torch.cuda.is_available():
         torch.cuda.set_device(local % torch.cuda.device_count())
     if world > 1 and not dist.is_initialized():
+        # NCCL writes its version/debug lines to stdout by default; callers print machine-readable
+        # results there, so send NCCL's own chatter to stderr unless the user chose a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
         backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")

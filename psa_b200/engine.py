@@ -43,7 +43,8 @@ class Engine:
         if project_impl is None:
             project_impl = int(os.environ.get("PSA_B200_PROJECT_IMPL", _lib.PROJECT_TENSOR))
         self.project_impl = project_impl
-        self._twiddles: Dict[int, torch.Tensor] = {}
+        self._plans: Dict[int, torch.Tensor] = {}
+        self._fft_ws: Optional[torch.Tensor] = None
         self.launches = 0          # kernels launched through this engine (bench reports it)
         self.profile: Optional[Dict[str, List[Tuple[torch.cuda.Event, torch.cuda.Event, int]]]] = None
 
@@ -108,19 +109,29 @@ class Engine:
                   expo.data_ptr(), n_t, n_sel, pitch, P.data_ptr(), ldp,
                   self.project_impl if impl is None else impl, self.stream())
 
-    def twiddles(self, n_t: int) -> torch.Tensor:
-        tw = self._twiddles.get(n_t)
-        if tw is None:
-            tw = self.empty((n_t, 2), torch.float32)
-            self._run("psa_twiddles", 1, n_t, tw.data_ptr(), self.stream())
-            self._twiddles[n_t] = tw
-        return tw
+    def fft_plan(self, n_t: int) -> torch.Tensor:
+        """Device-resident FFT plan for ``n_t`` frames (twiddles; chirp tables when n_t is not 2^s), cached."""
+        plan = self._plans.get(n_t)
+        if plan is None:
+            nbytes = int(_lib.load().psa_fft_plan_bytes(n_t))
+            if nbytes < 0:
+                _lib.check(_lib.ERR_UNSUPPORTED)
+            plan = self.empty((nbytes,), torch.uint8)
+            self._run("psa_fft_plan_init", 3, n_t, plan.data_ptr(), self.stream())
+            self._plans[n_t] = plan
+        return plan
 
     def fft_sed(self, P: torch.Tensor, n_groups: int, group_stride: int, n_k: int, n_t: int, ldp: int,
                 mode: int, out: torch.Tensor, n_k_total: int, k_offset: int) -> None:
-        tw = self.twiddles(n_t)
-        self._run("psa_fft_sed", 1, P.data_ptr(), n_groups, group_stride, n_k, n_t, ldp, tw.data_ptr(), mode,
-                  out.data_ptr(), n_k_total, k_offset, self.stream())
+        plan = self.fft_plan(n_t)
+        ws_bytes = int(_lib.load().psa_fft_workspace_bytes(n_t, n_k, n_groups))
+        ws = None
+        if ws_bytes > 0:
+            if self._fft_ws is None or self._fft_ws.numel() < ws_bytes:
+                self._fft_ws = self.empty((ws_bytes,), torch.uint8)
+            ws = self._fft_ws
+        self._run("psa_fft_sed", 1 if ws is None else 2, P.data_ptr(), n_groups, group_stride, n_k, n_t, ldp,
+                  plan.data_ptr(), _ptr(ws), ws_bytes, mode, out.data_ptr(), n_k_total, k_offset, self.stream())
 
     def chiral_phase(self, z1: torch.Tensor, z2: torch.Tensor, n: int, stride1: int, stride2: int, opt: str,
                      out: torch.Tensor) -> None:

@@ -185,10 +185,32 @@ def test_fft_incoherent(eng, n_t):
     np.testing.assert_allclose(out.cpu().numpy(), want, rtol=2e-5, atol=1e-6 * want.max())
 
 
+@pytest.mark.parametrize("n_t", [2, 7, 16, 250, 1000, 3001, 8191, 10000, 20000])
+def test_fft_any_length_bluestein(eng, n_t):
+    """Frame counts that are not a power of two (the reference accepts any n_t) go through Bluestein."""
+    rng = np.random.default_rng(n_t)
+    n_k, ldp = 2, -(-n_t // 4) * 4
+    P = np.zeros((2 * n_k, 3, ldp), np.float32)
+    P[:, :, :n_t] = rng.standard_normal((2 * n_k, 3, n_t))
+    out = torch.zeros((n_t, n_k, 3), dtype=torch.complex64, device=eng.device)
+    eng.fft_sed(dev(eng, P), 1, P.size, n_k, n_t, ldp, 0, out, n_k, 0)
+    z = P[0::2, :, :n_t].astype(np.float64) + 1j * P[1::2, :, :n_t].astype(np.float64)
+    want = (np.fft.fft(z, axis=-1) / n_t).transpose(2, 0, 1)
+    assert np.abs(out.cpu().numpy() - want).max() < 6e-6 * np.abs(want).max()
+    # incoherent assembly over two groups through the same path
+    Pg = np.stack([P, P[::-1].copy()])
+    acc = torch.zeros((n_t, n_k), dtype=torch.float32, device=eng.device)
+    eng.fft_sed(dev(eng, Pg), 2, P.size, n_k, n_t, ldp, 1, acc, n_k, 0)
+    zg = Pg[:, 0::2, :, :n_t].astype(np.float64) + 1j * Pg[:, 1::2, :, :n_t].astype(np.float64)
+    want_i = (np.abs(np.fft.fft(zg, axis=-1) / n_t) ** 2).sum(axis=(0, 2)).T
+    np.testing.assert_allclose(acc.cpu().numpy(), want_i, rtol=5e-5, atol=2e-6 * want_i.max())
+
+
 def test_fft_rejects_unsupported_length(eng):
-    out = torch.zeros((250, 1, 3), dtype=torch.complex64, device=eng.device)
+    from psa_b200 import _lib
+    assert _lib.load().psa_fft_plan_bytes(1) == -1 and _lib.load().psa_fft_plan_bytes(2 ** 19 + 1) == -1
     with pytest.raises(NotImplementedError):
-        eng.fft_sed(torch.zeros((2, 3, 252), device=eng.device), 1, 0, 1, 250, 252, 0, out, 1, 0)
+        eng.fft_plan(2 ** 19 + 1)
 
 
 # ------------------------------------------------------------------ element-wise kernels
@@ -355,15 +377,19 @@ def test_ised_reconstructor_facade(gold_si, tmp_path):
     assert (tmp_path / "x.dump").exists()
 
 
-def test_odd_frame_count_is_reported_not_faked(gold_si):
+def test_odd_frame_count_matches_reference(gold_si):
+    """250 frames: not a power of two -> Bluestein path, checked against the real reference's output."""
     from psa_b200 import SEDCalculator, Trajectory
     g = gold_si
     box = g["box_matrix"]
     traj = Trajectory(g["positions"][:250], g["velocities"][:250], g["types"], np.arange(250), box,
                       np.diag(box).copy(), np.zeros(3, np.float32), float(g["dt_ps"]))
     calc = SEDCalculator(traj, 2, 2, 2)
-    with pytest.raises(NotImplementedError):
-        calc.calculate(g["kpath_100_mags"], g["kpath_100_vecs"])
+    res = calc.calculate(g["kpath_100_mags"], g["kpath_100_vecs"])
+    ref = g["sed_odd250_coh_all_100"]
+    assert res.sed.shape == ref.shape
+    assert np.abs(res.sed - ref).max() < 4e-6 * np.abs(ref).max()
+    np.testing.assert_array_equal(res.freqs, np.fft.fftfreq(250, d=float(g["dt_ps"])))
 
 
 # ------------------------------------------------------------------ medium size: three-distance parity report
