@@ -34,6 +34,7 @@ extern "C" {
 /* psa_project() kernels */
 #define PSA_PROJECT_TENSOR 0   /* tcgen05 int8 tensor-core kernel (the product path)      */
 #define PSA_PROJECT_SIMT 1     /* dp4a CUDA-core kernel, same exact result (bring-up/validation) */
+#define PSA_PROJECT_TENSOR_PAIR 2 /* tcgen05 cta_group::2 variant of the tensor-core kernel (same result) */
 
 int psa_version(void);
 const char* psa_last_error(void);

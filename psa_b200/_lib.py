@@ -22,6 +22,7 @@ MODE_COHERENT = 0
 MODE_INCOHERENT = 1
 PROJECT_TENSOR = 0
 PROJECT_SIMT = 1
+PROJECT_TENSOR_PAIR = 2
 
 LIB_PATH = Path(__file__).resolve().parent / "libpsa_b200.so"
 

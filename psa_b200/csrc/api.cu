@@ -81,6 +81,8 @@ int psa_project(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8
               "psa_project: buffers must be 16-byte aligned");
   if (impl == PSA_PROJECT_TENSOR)
     return launch_project_tc(adig, rows, rows_alloc, bdig, expo, n_t, n_sel, pitch, P, ldp, as_stream(stream));
+  if (impl == PSA_PROJECT_TENSOR_PAIR)
+    return launch_project_tc2(adig, rows, rows_alloc, bdig, expo, n_t, n_sel, pitch, P, ldp, as_stream(stream));
   if (impl == PSA_PROJECT_SIMT)
     return launch_project_simt(adig, rows, rows_alloc, bdig, expo, n_t, n_sel, pitch, P, ldp, as_stream(stream));
   set_error("psa_project: unknown impl %d", impl);

@@ -69,6 +69,9 @@ int launch_phase_digits(const float* kvecs, int64_t n_k, const float* mean, cons
 int launch_project_tc(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig,
                       const int32_t* expo, int64_t n_t, int64_t n_sel, int64_t pitch, float* P,
                       int64_t ldp, cudaStream_t s);
+int launch_project_tc2(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig,
+                       const int32_t* expo, int64_t n_t, int64_t n_sel, int64_t pitch, float* P,
+                       int64_t ldp, cudaStream_t s);
 int launch_project_simt(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig,
                         const int32_t* expo, int64_t n_t, int64_t n_sel, int64_t pitch, float* P,
                         int64_t ldp, cudaStream_t s);

@@ -59,7 +59,12 @@ __device__ __forceinline__ void bfly4(float2& a0, float2& a1, float2& a2, float2
 // the power-of-two core
 // ---------------------------------------------------------------------------------------------
 // Shared-memory passes: reduce the m-point problem to m/32 independent contiguous 32-point blocks.
-__device__ void fft_smem_passes(float2* __restrict__ s, int m, int log2m, const float2* __restrict__ tw, int tw_n) {
+// Radix-4 pass twiddles come from per-pass tables (w_L^j, w_L^2j, w_L^3j stored contiguously in j), so
+// a warp reads three short contiguous runs instead of 96 scattered entries of the length-n table.
+__host__ __device__ inline int pass_table_base(int L) { return 3 * ((L >> 2) - 16); }   // entries before pass L (L >= 64)
+
+__device__ void fft_smem_passes(float2* __restrict__ s, int m, int log2m, const float2* __restrict__ tw, int tw_n,
+                                const float2* __restrict__ pass_tw) {
   int L = m;
   if ((log2m - 5) & 1) {   // radix-2 pass
     const int half = L >> 1, tstep = tw_n / L;
@@ -74,7 +79,10 @@ __device__ void fft_smem_passes(float2* __restrict__ s, int m, int log2m, const 
     __syncthreads();
   }
   for (; L > kBlk; L >>= 2) {
-    const int q = L >> 2, tstep = tw_n / L;
+    const int q = L >> 2;
+    const float2* __restrict__ t1 = pass_tw + pass_table_base(L);
+    const float2* __restrict__ t2 = t1 + q;
+    const float2* __restrict__ t3 = t2 + q;
 #pragma unroll 4
     for (int b = threadIdx.x; b < (m >> 2); b += blockDim.x) {
       const int j = b & (q - 1);
@@ -82,12 +90,9 @@ __device__ void fft_smem_passes(float2* __restrict__ s, int m, int log2m, const 
       const int i0 = phys(base), i1 = phys(base + q), i2 = phys(base + 2 * q), i3 = phys(base + 3 * q);
       float2 a0 = s[i0], a1 = s[i1], a2 = s[i2], a3 = s[i3];
       bfly4(a0, a1, a2, a3);
-      if (j != 0) {
-        const int64_t w = (int64_t)j * tstep;
-        a1 = cmul(a1, __ldg(tw + w));
-        a2 = cmul(a2, __ldg(tw + 2 * w));
-        a3 = cmul(a3, __ldg(tw + 3 * w));
-      }
+      a1 = cmul(a1, __ldg(t1 + j));
+      a2 = cmul(a2, __ldg(t2 + j));
+      a3 = cmul(a3, __ldg(t3 + j));
       s[i0] = a0; s[i1] = a1; s[i2] = a2; s[i3] = a3;
     }
     __syncthreads();
@@ -146,7 +151,8 @@ __device__ __forceinline__ int block_base_frequency(int b, int log2m) {
 // Geometry of one launch: transform length n_fft = m * R, twiddle table of length n_fft.
 struct FftGeom {
   int m, log2m, R, n_fft;
-  const float2* tw;
+  const float2* tw;        // w_n^j, j < n_fft
+  const float2* pass_tw;   // per-pass radix-4 tables, see pass_table_base
 };
 
 // Fill shared memory with sub-sequence r of the radix-R split of fetch(0..n_fft) (R == 1: plain copy).
@@ -172,7 +178,7 @@ __device__ void load_column(float2* __restrict__ s, const Fetch& fetch, const Ff
 // slot = padded in-place position, owned by the same thread on every call with the same geometry.
 template <class Sink>
 __device__ void transform_and_emit(float2* __restrict__ s, const FftGeom& g, int r, Sink& sink) {
-  fft_smem_passes(s, g.m, g.log2m, g.tw, g.n_fft);
+  fft_smem_passes(s, g.m, g.log2m, g.tw, g.n_fft, g.pass_tw);
   const int n_blocks = g.m >> 5, fstep = g.m >> 5;
   for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) {
     float2 x[kBlk];
@@ -415,9 +421,34 @@ __global__ void __launch_bounds__(kFftThreads) fft_c2c_kernel(const float2* __re
 
 // ---------------------------------------------------------------------------------------------
 // plan: twiddles (+ chirp and its spectrum for non-power-of-two lengths), one caller-owned buffer
-//   power of two : [ tw (n_t) ]
-//   otherwise    : [ tw (M) | chirp (n_t) | bhat (M) | work (M) ]      all float2
+//   power of two : [ tw (n_t) | pass tables ]
+//   otherwise    : [ tw (M)   | pass tables | chirp (n_t) | bhat (M) | work (M) ]      all float2
 // ---------------------------------------------------------------------------------------------
+static int64_t pass_table_entries(int64_t n_fft) {
+  const int64_t lmax = n_fft < kMaxSmemPoints ? n_fft : kMaxSmemPoints;
+  return lmax >= 64 ? pass_table_base((int)lmax) + 3 * (lmax >> 2) : 0;
+}
+
+__global__ void pass_table_kernel(int L, float2* __restrict__ table) {   // table already offset to pass L
+  const int q = L >> 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * q) return;
+  const int r = i / q + 1, j = i % q;
+  double s, c;
+  sincospi(2.0 * (double)((r * j) % L) / (double)L, &s, &c);
+  table[i] = make_float2((float)c, (float)(-s));
+}
+
+__global__ void twiddle_kernel(int64_t n, float2* __restrict__ tw);
+
+static int build_tables(int64_t n_fft, float2* tw, cudaStream_t s) {
+  twiddle_kernel<<<(unsigned)((n_fft + 255) / 256), 256, 0, s>>>(n_fft, tw);
+  float2* pass = tw + n_fft;
+  for (int64_t L = 64; L <= n_fft && L <= kMaxSmemPoints; L <<= 1)
+    pass_table_kernel<<<(unsigned)((3 * (L >> 2) + 255) / 256), 256, 0, s>>>((int)L, pass + pass_table_base((int)L));
+  return launch_status("fft table kernels");
+}
+
 __global__ void twiddle_kernel(int64_t n, float2* __restrict__ tw) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
@@ -450,7 +481,7 @@ static int64_t bluestein_length(int64_t n) {
   return m;
 }
 
-static FftGeom make_geom(int64_t n_fft, const float2* tw) {
+static FftGeom make_geom(int64_t n_fft, const float2* tw) {   // tw = start of the plan: [tw | pass tables | ...]
   static const int64_t max_points = []() -> int64_t {     // tuning knob, see profiles/
     const char* env = getenv("PSA_FFT_MAX_POINTS");
     int64_t v = env ? atoll(env) : kMaxSmemPoints;
@@ -467,6 +498,7 @@ static FftGeom make_geom(int64_t n_fft, const float2* tw) {
   g.log2m = 0;
   while ((1 << g.log2m) < m) ++g.log2m;
   g.tw = tw;
+  g.pass_tw = tw + n_fft;
   return g;
 }
 
@@ -487,10 +519,10 @@ int fft_plan_bytes(int64_t n_t, int64_t* bytes) {
     return PSA_ERR_UNSUPPORTED;
   }
   if (is_pow2(n_t) && n_t >= kBlk) {
-    *bytes = n_t * (int64_t)sizeof(float2);
+    *bytes = (n_t + pass_table_entries(n_t)) * (int64_t)sizeof(float2);
   } else {
     const int64_t M = bluestein_length(n_t);
-    *bytes = (3 * M + round_up(n_t, 2)) * (int64_t)sizeof(float2);
+    *bytes = (3 * M + pass_table_entries(M) + round_up(n_t, 2)) * (int64_t)sizeof(float2);
   }
   return PSA_OK;
 }
@@ -499,16 +531,13 @@ int launch_fft_plan(int64_t n_t, float2* plan, cudaStream_t s) {
   int64_t bytes = 0;
   int st = fft_plan_bytes(n_t, &bytes);
   if (st != PSA_OK) return st;
-  if (is_pow2(n_t) && n_t >= kBlk) {
-    twiddle_kernel<<<(unsigned)((n_t + 255) / 256), 256, 0, s>>>(n_t, plan);
-    return launch_status("twiddle_kernel");
-  }
+  if (is_pow2(n_t) && n_t >= kBlk) return build_tables(n_t, plan, s);
   const int64_t M = bluestein_length(n_t);
   float2* tw = plan;
-  float2* chirp = tw + M;
+  float2* chirp = tw + M + pass_table_entries(M);
   float2* bhat = chirp + round_up(n_t, 2);
   float2* work = bhat + M;
-  twiddle_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(M, tw);
+  if ((st = build_tables(M, tw, s)) != PSA_OK) return st;
   chirp_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(n_t, M, chirp, work);
   FftGeom g = make_geom(M, tw);
   st = allow_smem(fft_c2c_kernel, smem_bytes(g, false));
@@ -554,7 +583,7 @@ int launch_fft(const float* P, int64_t n_groups, int64_t group_stride, int64_t n
 
   const int64_t M = bluestein_length(n_t);
   const float2* tw = plan;
-  const float2* chirp = tw + M;
+  const float2* chirp = tw + M + pass_table_entries(M);
   const float2* bhat = chirp + round_up(n_t, 2);
   float2* scratch = reinterpret_cast<float2*>(workspace);
   FftGeom g = make_geom(M, tw);

@@ -11,18 +11,19 @@ namespace psa {
 // SURVEY.md appendix A).
 // ---------------------------------------------------------------------------------------------
 // The adds of one column are inherently serial, so bandwidth has to come from memory-level
-// parallelism instead: a CTA owns 32 adjacent columns (one 128-byte line per frame); all 8 warps
-// stream a tile of 128 frames into registers (16 independent coalesced loads per thread, issued
+// parallelism instead: a CTA owns 32 adjacent columns (one 128-byte line per frame); all 16 warps
+// stream a tile of 256 frames into registers (16 independent coalesced loads per thread, issued
 // while the previous tile is being consumed), park it in shared memory, and warp 0 then performs
 // the ordered float32 additions from shared memory.
 constexpr int kMeanCols = 32;
-constexpr int kMeanRows = 128;
-constexpr int kMeanThreads = 256;
+constexpr int kMeanRows = 256;
+constexpr int kMeanThreads = 512;
 constexpr int kMeanPerThread = kMeanRows / (kMeanThreads / 32);   // 16 rows per thread per tile
 
 __global__ void __launch_bounds__(kMeanThreads) mean_positions_kernel(const float* __restrict__ pos, int64_t n_t,
                                                                       int64_t n_cols, float* __restrict__ mean) {
-  __shared__ float tile[2][kMeanRows][kMeanCols];
+  extern __shared__ float mean_smem[];
+  float (*tile)[kMeanRows][kMeanCols] = reinterpret_cast<float (*)[kMeanRows][kMeanCols]>(mean_smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t col = (int64_t)blockIdx.x * kMeanCols + lane;
   const bool col_ok = col < n_cols;
@@ -66,7 +67,9 @@ int launch_mean_positions(const float* pos, int64_t n_t, int64_t n_a, float* mea
   int64_t n_cols = n_a * 3;
   if (n_cols == 0) return PSA_OK;
   int64_t blocks = (n_cols + kMeanCols - 1) / kMeanCols;
-  mean_positions_kernel<<<(unsigned)blocks, kMeanThreads, 0, s>>>(pos, n_t, n_cols, mean);
+  constexpr int smem = 2 * kMeanRows * kMeanCols * (int)sizeof(float);   // 64 KiB: three CTAs per SM
+  PSA_CUDA(cudaFuncSetAttribute(mean_positions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  mean_positions_kernel<<<(unsigned)blocks, kMeanThreads, smem, s>>>(pos, n_t, n_cols, mean);
   return launch_status("mean_positions_kernel");
 }
 
@@ -76,11 +79,38 @@ int launch_mean_positions(const float* pos, int64_t n_t, int64_t n_a, float* mea
 // rint(x * 2^(30-e)) as four int8 planes dig[pol][slice][t][atom].  A thread handles four
 // consecutive atoms so that every plane store is a packed 32-bit word.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float load_value(const float* __restrict__ row, const float* __restrict__ mean,
-                                            int64_t atom, int pol) {
-  float v = __ldg(row + atom * 3 + pol);
-  if (mean != nullptr) v = __fsub_rn(v, __ldg(mean + atom * 3 + pol));
-  return v;
+// Values of four consecutive selected atoms (12 floats).  Without a gather list the 48 bytes are
+// contiguous and, when 16-byte aligned, fetched as three float4 loads; otherwise scalar loads.
+__device__ __forceinline__ void load_quad(const float* __restrict__ row, const float* __restrict__ mean,
+                                          const int32_t* __restrict__ idx, int64_t j0, int64_t n_sel, float (&v)[12]) {
+  const float* src = row + j0 * 3;
+  if (idx == nullptr && j0 + 4 <= n_sel && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4 a = __ldg(s4), b = __ldg(s4 + 1), c = __ldg(s4 + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y;
+    v[6] = b.z; v[7] = b.w; v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+    if (mean != nullptr) {
+      const float* m = mean + j0 * 3;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) v[i] = __fsub_rn(v[i], __ldg(m + i));
+    }
+    return;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int64_t j = j0 + q;
+    if (j < n_sel) {
+      const int64_t atom = idx ? (int64_t)__ldg(idx + j) : j;
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        float x = __ldg(row + atom * 3 + p);
+        if (mean != nullptr) x = __fsub_rn(x, __ldg(mean + atom * 3 + p));
+        v[q * 3 + p] = x;
+      }
+    } else {
+      v[q * 3] = v[q * 3 + 1] = v[q * 3 + 2] = 0.f;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) digitize_kernel(const float* __restrict__ data,
@@ -94,10 +124,23 @@ __global__ void __launch_bounds__(256) digitize_kernel(const float* __restrict__
   __shared__ int s_exp[3];
 
   float mx[3] = {0.f, 0.f, 0.f};
-  for (int64_t j = threadIdx.x; j < n_sel; j += blockDim.x) {
-    int64_t atom = idx ? (int64_t)__ldg(idx + j) : j;
+  if (idx == nullptr) {
+    for (int64_t j0 = (int64_t)threadIdx.x * 4; j0 < n_sel; j0 += (int64_t)blockDim.x * 4) {
+      float v[12];
+      load_quad(row, mean, idx, j0, n_sel, v);
 #pragma unroll
-    for (int p = 0; p < 3; ++p) mx[p] = fmaxf(mx[p], fabsf(load_value(row, mean, atom, p)));
+      for (int i = 0; i < 12; ++i) mx[i % 3] = fmaxf(mx[i % 3], fabsf(v[i]));
+    }
+  } else {   // gather: one selected atom per thread keeps neighbouring lanes on neighbouring atoms
+    for (int64_t j = threadIdx.x; j < n_sel; j += blockDim.x) {
+      const int64_t atom = (int64_t)__ldg(idx + j);
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        float x = __ldg(row + atom * 3 + p);
+        if (mean != nullptr) x = __fsub_rn(x, __ldg(mean + atom * 3 + p));
+        mx[p] = fmaxf(mx[p], fabsf(x));
+      }
+    }
   }
 #pragma unroll
   for (int p = 0; p < 3; ++p) {
@@ -126,20 +169,18 @@ __global__ void __launch_bounds__(256) digitize_kernel(const float* __restrict__
   const int64_t plane = n_t * pitch;                 // bytes of one (pol, slice) plane
   for (int64_t j0 = (int64_t)threadIdx.x * 4; j0 < pitch; j0 += (int64_t)blockDim.x * 4) {
     uint32_t word[3][kSlices] = {};
+    if (j0 < n_sel) {
+      float v[12];
+      load_quad(row, mean, idx, j0, n_sel, v);      // entries past n_sel come back as zeros -> zero digits
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      int64_t j = j0 + q;
-      if (j < n_sel) {
-        int64_t atom = idx ? (int64_t)__ldg(idx + j) : j;
+      for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
-          float v = load_value(row, mean, atom, p);
           int8_t d[kSlices];
-          balanced_digits(__float2int_rn(v * scale[p]), d);
+          balanced_digits(__float2int_rn(v[q * 3 + p] * scale[p]), d);
 #pragma unroll
           for (int sl = 0; sl < kSlices; ++sl) word[p][sl] |= (uint32_t)(uint8_t)d[sl] << (8 * q);
         }
-      }
     }
 #pragma unroll
     for (int p = 0; p < 3; ++p)

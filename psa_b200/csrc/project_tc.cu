@@ -92,6 +92,39 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One lane of a fully converged warp.  ptxas only emits straight-line UTCIMMA / UTMALDG code when the
+// single issuing thread is chosen with elect.sync; under a plain `lane == 0` branch it wraps every
+// uniform-datapath instruction in an ELECT/branch loop that costs more than the MMA itself.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// MMA with descriptors given as (low word, shared high word): the low word is linear in the smem
+// address, so stepping through slices / K steps is one 32-bit add per operand.
+__device__ __forceinline__ void tc_mma_i8_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n"
+      "}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
+constexpr uint32_t kDescHi = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);   // SBO, version 1, SWIZZLE_64B
+
 #define PSA_TMEM_LD16(r, addr)                                                                         \
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),   \
@@ -109,16 +142,22 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
 }
 
 struct TileCoord {
-  int r_tile, pol, t_tile, n_cols;   // n_cols: valid phase rows in this tile, rounded up to 16
+  int r_tile, pol, t_tile, row0, n_cols;   // row0: first phase row; n_cols: rows in this tile, rounded up to 16
 };
+// Phase rows are spread evenly over the row tiles (each a multiple of 16 columns, at most 128): a
+// 400-row k-path becomes 4 x 112 columns instead of 3 x 128 + 16 - a 16-column tile costs almost as
+// much as a full one because the M-side operand read does not shrink with N.
 __device__ __forceinline__ TileCoord decode_tile(int tile, int r_tiles, int t_tiles, int rows) {
   TileCoord c;
   c.r_tile = tile % r_tiles;          // row tiles fastest: concurrent CTAs share the same trajectory strip
   int n = tile / r_tiles;
   c.pol = n / t_tiles;
   c.t_tile = n % t_tiles;
-  int left = rows - c.r_tile * BN;
-  c.n_cols = left >= BN ? BN : ((left + 15) & ~15);
+  const int per_tile = (((rows + r_tiles - 1) / r_tiles) + 15) & ~15;
+  c.row0 = c.r_tile * per_tile;
+  int left = rows - c.row0;
+  left = left < 0 ? 0 : left;
+  c.n_cols = left >= per_tile ? per_tile : ((left + 15) & ~15);
   return c;
 }
 
@@ -159,37 +198,40 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int total_tiles = r_tiles * t_tiles * 3;
   const int num_kb = (a_end - a_begin + BK - 1) / BK;
 
-  if (warp == 0) {
-    if (lane == 0) {                                           // ---------------- TMA producer
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        TileCoord tc = decode_tile(tile, r_tiles, t_tiles, rows);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+  if (warp == 0) {                                             // ---------------- TMA producer (one elected lane)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(tile, r_tiles, t_tiles, rows);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          uint32_t dst = smem_u32(smem + stage * STAGE_BYTES);
-          int atom0 = a_begin + kb * BK;
+          const uint32_t dst = smem_u32(smem + stage * STAGE_BYTES);
+          const int atom0 = a_begin + kb * BK;
           tma_load_3d(dst, &tmap_b, &full_bar[stage], atom0, tc.t_tile * BM, tc.pol * kSlices);   // M side
-          tma_load_3d(dst + OPERAND_BYTES, &tmap_a, &full_bar[stage], atom0, tc.r_tile * BN, 0);    // N side
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          tma_load_3d(dst + OPERAND_BYTES, &tmap_a, &full_bar[stage], atom0, tc.row0, 0);            // N side
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {                                           // ---------------- MMA issuer
-      int stage = 0;
-      uint32_t phase = 0, tile_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(tile, r_tiles, t_tiles, rows);
-        const uint32_t idesc = make_idesc(tc.n_cols);
-        mbar_wait(tmem_empty, tile_phase ^ 1);                 // epilogue has drained the accumulators
+  } else if (warp == 1) {                                      // ---------------- MMA issuer (one elected lane)
+    int stage = 0;
+    uint32_t phase = 0, tile_phase = 0;
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem));            // stage 0, slice 0, K step 0 of the M-side operand
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(tile, r_tiles, t_tiles, rows);
+      const uint32_t idesc = make_idesc(tc.n_cols);
+      mbar_wait(tmem_empty, tile_phase ^ 1);                   // epilogue has drained the accumulators
+      tc_fence_after();
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);   // trajectory digits (M side)
-          const uint32_t b_base = a_base + OPERAND_BYTES;                 // phase digits (N side)
+        if (elect_one()) {
+          const uint32_t a_lo = a_lo0 + (uint32_t)((stage * STAGE_BYTES) >> 4);   // trajectory digits (M side)
+          const uint32_t b_lo = a_lo + (uint32_t)(OPERAND_BYTES >> 4);            // phase digits (N side)
+          const uint32_t first = kb > 0 ? 1u : 0u;
 #pragma unroll
           for (int ks = 0; ks < BK / UMMA_K; ++ks) {
 #pragma unroll
@@ -197,21 +239,21 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
               for (int sj = 0; sj < kSlices; ++sj) {
                 if (si + sj < kMinClass) continue;
-                const uint64_t da = smem_desc(a_base + si * SLICE_BYTES + ks * UMMA_K);
-                const uint64_t db = smem_desc(b_base + sj * SLICE_BYTES + ks * UMMA_K);
                 const uint32_t d = tmem_base + (uint32_t)((si + sj - kMinClass) * BN);
-                // the first product issued into each class (sj == 3) overwrites, the rest accumulate
-                const uint32_t acc = (kb > 0 || ks > 0 || sj != kSlices - 1) ? 1u : 0u;
-                tc_mma_i8(d, da, db, idesc, acc);
+                // the first product issued into each class of a tile (ks == 0, sj == 3) overwrites
+                const uint32_t acc = (ks > 0 || sj != kSlices - 1) ? 1u : first;
+                tc_mma_i8_lohi(d, a_lo + (uint32_t)((si * SLICE_BYTES + ks * UMMA_K) >> 4),
+                               b_lo + (uint32_t)((sj * SLICE_BYTES + ks * UMMA_K) >> 4), kDescHi, idesc, acc);
               }
             }
           }
           tc_commit(&empty_bar[stage]);                        // stage reusable once these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (kb == num_kb - 1) tc_commit(tmem_full);          // accumulators complete
         }
-        tc_commit(tmem_full);                                  // accumulators complete
-        tile_phase ^= 1;
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      tile_phase ^= 1;
     }
   } else {                                                     // ---------------- epilogue warps 2..9
     const int quarter = warp & 3;                              // TMEM lane quarter this warp may read
@@ -235,7 +277,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         PSA_TMEM_LD16(r3, lane_addr + 3 * BN + c0);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (t_ok) {
-          const int row0 = tc.r_tile * BN + c0;
+          const int row0 = tc.row0 + c0;
           float* dst = P + ((int64_t)row0 * 3 + tc.pol) * ldp + t;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {

@@ -41,7 +41,7 @@ class Engine:
         self.device = torch.device("cuda", device)
         _lib.check(_lib.load().psa_device_check(device))
         if project_impl is None:
-            project_impl = int(os.environ.get("PSA_B200_PROJECT_IMPL", _lib.PROJECT_TENSOR))
+            project_impl = int(os.environ.get("PSA_B200_PROJECT_IMPL", _lib.PROJECT_TENSOR_PAIR))
         self.project_impl = project_impl
         self._plans: Dict[int, torch.Tensor] = {}
         self._fft_ws: Optional[torch.Tensor] = None

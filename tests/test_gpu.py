@@ -133,6 +133,15 @@ def test_project_tensor_matches_integer_model(eng, rows, n_t, n_sel):
     np.testing.assert_array_equal(got, M.project(xa, xb, e))
 
 
+@pytest.mark.parametrize("rows,n_t,n_sel", SHAPES + [(400, 1024, 2048), (16, 256, 128)])
+def test_project_tensor_pair_matches_integer_model(eng, rows, n_t, n_sel):
+    """cta_group::2 variant (two CTAs share one 256-frame tile): same bits."""
+    from psa_b200 import _lib
+    xa, xb, e = _proj_inputs(np.random.default_rng(rows * 5 + n_t), rows, n_t, n_sel)
+    got = _run_project(eng, xa, xb, e, _lib.PROJECT_TENSOR_PAIR, rows_alloc=rows + 10)
+    np.testing.assert_array_equal(got, M.project(xa, xb, e))
+
+
 def test_project_extreme_digits_no_overflow(eng):
     """Worst-case digits (every product at its maximum) over a full 32768-atom pass stay exact."""
     from psa_b200 import _lib
