@@ -101,7 +101,8 @@ int64_t psa_fft_workspace_bytes(int64_t n_t, int64_t n_k, int64_t n_groups) {
 
 int psa_fft_plan_init(int64_t n_t, void* plan, void* stream) {
   PSA_REQUIRE(plan != nullptr, "psa_fft_plan_init: null plan buffer");
-  return launch_fft_plan(n_t, reinterpret_cast<float2*>(plan), as_stream(stream));
+  PSA_REQUIRE(((uintptr_t)plan % 16) == 0, "psa_fft_plan_init: plan buffer must be 16-byte aligned");
+  return launch_fft_plan(n_t, plan, as_stream(stream));
 }
 
 int psa_fft_sed(const float* P, int64_t n_groups, int64_t group_stride, int64_t n_k, int64_t n_t, int64_t ldp,
@@ -111,8 +112,8 @@ int psa_fft_sed(const float* P, int64_t n_groups, int64_t group_stride, int64_t 
   PSA_REQUIRE(n_groups >= 1 && n_k > 0 && n_t > 0 && ldp >= n_t, "psa_fft_sed: bad extents");
   PSA_REQUIRE(k_offset >= 0 && k_offset + n_k <= n_k_total, "psa_fft_sed: k range outside the result");
   PSA_REQUIRE(mode == PSA_MODE_INCOHERENT || n_groups == 1, "psa_fft_sed: coherent mode takes one group");
-  return launch_fft(P, n_groups, group_stride, n_k, n_t, ldp, reinterpret_cast<const float2*>(plan), workspace,
-                    workspace_bytes, mode, out, n_k_total, k_offset, as_stream(stream));
+  return launch_fft(P, n_groups, group_stride, n_k, n_t, ldp, plan, workspace, workspace_bytes, mode, out, n_k_total,
+                    k_offset, as_stream(stream));
 }
 
 int psa_chiral_phase(const float* z1, const float* z2, int64_t n, int64_t stride1, int64_t stride2, int opt,

@@ -77,9 +77,9 @@ int launch_project_simt(const int8_t* adig, int64_t rows, int64_t rows_alloc, co
                         int64_t ldp, cudaStream_t s);
 int fft_plan_bytes(int64_t n_t, int64_t* bytes);
 int fft_workspace_bytes(int64_t n_t, int64_t n_k, int64_t n_groups, int64_t* bytes);
-int launch_fft_plan(int64_t n_t, float2* plan, cudaStream_t s);
+int launch_fft_plan(int64_t n_t, void* plan, cudaStream_t s);
 int launch_fft(const float* P, int64_t n_groups, int64_t group_stride, int64_t n_k, int64_t n_t, int64_t ldp,
-               const float2* plan, void* workspace, int64_t workspace_bytes, int mode, void* out, int64_t n_k_total,
+               const void* plan, void* workspace, int64_t workspace_bytes, int mode, void* out, int64_t n_k_total,
                int64_t k_offset, cudaStream_t s);
 int launch_chiral(const float2* z1, const float2* z2, int64_t n, int64_t stride1, int64_t stride2,
                   int opt, float* out, cudaStream_t s);
