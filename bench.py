@@ -265,11 +265,32 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # Every rank needs the raw trajectory resident in HBM for the weak-scaling `value`.  Small workloads are
+    # generated by every rank (same seed); large ones are generated once on rank 0 and copied GPU-to-GPU
+    # (setup, untimed) so that host memory holds one copy only.
     t_gen = time.time()
-    traj = pinned_trajectory(spec)
-    log(f"[bench r{rank}] generated {cfg['desc']} in {time.time() - t_gen:.1f}s")
+    traj_bytes = 2 * spec.n_frames * spec.n_atoms * 12
+    share = world > 1 and traj_bytes > (4 << 30)
+    resident = None
+    if rank == 0 or not share:
+        traj = pinned_trajectory(spec)
+    else:
+        zero = np.broadcast_to(np.zeros(1, np.float32), (spec.n_frames, spec.n_atoms, 3))
+        traj = spec.wrap(zero, zero)
+    log(f"[bench r{rank}] generated {cfg['desc']} in {time.time() - t_gen:.1f}s (shared={share})")
     calc = SEDCalculator(traj, *spec.cells, device=dev.index)
     eng = calc.engine
+    if share:
+        from psa_b200.engine import DeviceTrajectory
+        shape = (spec.n_frames, spec.n_atoms, 3)
+        resident = []
+        for arr in (traj.positions, traj.velocities):
+            t = torch.empty(shape, dtype=torch.float32, device=dev)
+            if rank == 0:
+                t.copy_(torch.from_numpy(arr), non_blocking=True)
+            dist.broadcast(t, src=0)
+            resident.append(t)
+        calc._dev_traj = DeviceTrajectory(eng, resident[0], resident[1])
     jobs = build_jobs(cfg, calc, k_mult=world)
     slices = [pdist.shard_range(len(j[1]), rank, world) for j in jobs]
 

@@ -12,10 +12,11 @@ from dataclasses import dataclass
 
 import numpy as np
 
-
-def _require(cond: bool, msg: str) -> None:
-    if not cond:
-        raise ValueError(msg)
+# (field, required shape suffix or ndim, message) checked in order; the first violation raises ValueError
+_PER_FRAME_VECTORS = ("positions", "velocities")
+_FIXED_SHAPES = (("box_matrix", (3, 3), "Box matrix must be 3x3, got {shape}"),
+                 ("box_lengths", (3,), "Box lengths must be a 3-element array, got {shape}"),
+                 ("box_tilts", (3,), "Box tilts must be a 3-element array, got {shape}"))
 
 
 @dataclass
@@ -30,24 +31,27 @@ class Trajectory:
     dt_ps: float               # sampling interval, picoseconds
 
     def __post_init__(self) -> None:
-        for name in ("positions", "velocities"):
+        first = next(self._violations(), None)
+        if first is not None:
+            raise ValueError(first)
+
+    def _violations(self):
+        for name in _PER_FRAME_VECTORS:
             arr = getattr(self, name)
-            _require(arr.ndim == 3 and arr.shape[2] == 3,
-                     f"{name.capitalize()} must be 3D (frames, atoms, xyz) and last dimension must be 3.")
-        _require(self.types.ndim == 1, "Types must be 1D")
-        _require(self.timesteps.ndim == 1, "Timesteps must be 1D")
-        n_fr = len(self.timesteps)
-        _require(self.positions.shape[0] == n_fr and self.velocities.shape[0] == n_fr,
-                 "Frame count mismatch: positions, velocities, timesteps.")
-        n_at = len(self.types)
-        _require(self.positions.shape[1] == n_at and self.velocities.shape[1] == n_at,
-                 "Atom count mismatch: positions, velocities, types.")
-        _require(self.box_matrix.shape == (3, 3),
-                 f"Box matrix must be 3x3, got {self.box_matrix.shape}")
-        _require(self.box_lengths.shape == (3,),
-                 f"Box lengths must be a 3-element array, got {self.box_lengths.shape}")
-        _require(self.box_tilts.shape == (3,),
-                 f"Box tilts must be a 3-element array, got {self.box_tilts.shape}")
+            if arr.ndim != 3 or arr.shape[2] != 3:
+                yield f"{name.capitalize()} must be 3D (frames, atoms, xyz) and last dimension must be 3."
+        for name in ("types", "timesteps"):
+            if getattr(self, name).ndim != 1:
+                yield f"{name.capitalize()} must be 1D"
+        counts = {name: getattr(self, name).shape[:2] for name in _PER_FRAME_VECTORS}
+        if any(c[:1] != (len(self.timesteps),) for c in counts.values()):
+            yield "Frame count mismatch: positions, velocities, timesteps."
+        if any(c[1:2] != (len(self.types),) for c in counts.values()):
+            yield "Atom count mismatch: positions, velocities, types."
+        for name, want, msg in _FIXED_SHAPES:
+            shape = getattr(self, name).shape
+            if shape != want:
+                yield msg.format(shape=shape)
 
     @property
     def n_frames(self) -> int:

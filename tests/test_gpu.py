@@ -468,3 +468,22 @@ def test_k_sharded_two_gpus_equals_single_gpu():
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "MULTIGPU_CHECK world=2 results=[True, True, True]" in out.stdout
+
+
+def test_npy_cache_streams_to_device(gold_si, tmp_path):
+    """N1: a memory-mapped .npy cache goes through the chunked pinned-staging upload and gives the same bits."""
+    from psa_b200 import SEDCalculator, cache
+    from psa_b200 import engine as E
+    calc = _calc(gold_si)
+    cache.save_npy_cache(calc.traj, tmp_path / "run.lammpstrj")
+    mapped = cache.load_npy_cache(tmp_path / "run.lammpstrj", dt=float(gold_si["dt_ps"]))
+    old = E._UPLOAD_CHUNK_BYTES
+    E._UPLOAD_CHUNK_BYTES = 40_000            # force several staging chunks on this small trajectory
+    try:
+        calc_m = SEDCalculator(mapped, *[int(c) for c in gold_si["cells"]])
+        kv = gold_si["kpath_110_vecs"]
+        a = calc_m.calculate(np.zeros(len(kv)), kv).sed
+    finally:
+        E._UPLOAD_CHUNK_BYTES = old
+    b = calc.calculate(np.zeros(len(kv)), kv).sed
+    np.testing.assert_array_equal(a, b)

@@ -186,3 +186,36 @@ def test_trajectory_validation():
                      ("box_matrix", np.eye(2)), ("box_lengths", np.ones(2)), ("box_tilts", np.ones(4))):
         with pytest.raises(ValueError):
             Trajectory(**{**ok, key: bad})
+
+
+def test_npy_cache_roundtrip_matches_reference_loader(tmp_path, gold_si):
+    """N1: the .npy cache bundle is read (memory-mapped) with the reference loader's field semantics."""
+    from psa_b200 import Trajectory
+    from psa_b200 import cache
+    g = gold_si
+    box = g["box_matrix"]
+    traj = Trajectory(g["positions"][:16], g["velocities"][:16], g["types"], np.arange(16), box,
+                      np.diag(box).copy(), np.zeros(3, np.float32), 0.002)
+    fake = tmp_path / "run.lammpstrj"
+    assert not cache.has_npy_cache(fake)
+    with pytest.raises(FileNotFoundError):
+        cache.load_npy_cache(fake, 0.002)
+    cache.save_npy_cache(traj, fake)
+    assert cache.has_npy_cache(fake)
+    back = cache.load_npy_cache(fake, dt=0.002)
+    assert isinstance(back.positions, np.memmap) and back.positions.flags.writeable
+    np.testing.assert_array_equal(back.positions, traj.positions)
+    np.testing.assert_array_equal(back.velocities, traj.velocities)
+    np.testing.assert_array_equal(back.timesteps, np.arange(16, dtype=np.float32) * 0.002)
+    assert back.dt_ps == 0.002 and back.n_atoms == traj.n_atoms
+    # same answer as the reference's own loader, when the reference is on this machine
+    from oracle.ref_import import load_reference
+    psa = load_reference()
+    if psa is not None:
+        fake.write_text("placeholder: the loader only checks that the file exists before using the cache\n")
+        ref = psa.TrajectoryLoader(str(fake), dt=0.002).load()
+        for name in ("positions", "velocities", "types", "timesteps", "box_matrix", "box_lengths", "box_tilts"):
+            np.testing.assert_array_equal(getattr(back, name), getattr(ref, name), err_msg=name)
+        assert ref.dt_ps == back.dt_ps
+    with pytest.raises(ValueError):
+        cache.load_npy_cache(fake, dt=0.0)
