@@ -82,16 +82,6 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
-      "}\n"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // One lane of a fully converged warp.  ptxas only emits straight-line UTCIMMA / UTMALDG code when the
 // single issuing thread is chosen with elect.sync; under a plain `lane == 0` branch it wraps every
 // uniform-datapath instruction in an ELECT/branch loop that costs more than the MMA itself.
@@ -131,11 +121,9 @@ constexpr uint32_t kDescHi = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);   /
                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) \
                : "r"(addr))
 
-// Shared-memory matrix descriptor, K-major operand, 64-byte swizzle: rows of 64 B, 8-row groups
-// 512 B apart (SBO), descriptor version 1 (sm_100), layout type 4 = SWIZZLE_64B.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
-}
+// Shared-memory matrix descriptors (K-major operand, 64-byte swizzle: rows of 64 B, 8-row groups 512 B
+// apart = SBO, descriptor version 1 for sm_100, layout type 4 = SWIZZLE_64B) are built from desc_lo /
+// kDescHi above.
 // Instruction descriptor: D = s32, A = B = s8, both K-major, M = 128, N = n (multiple of 16).
 __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);

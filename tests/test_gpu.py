@@ -487,3 +487,75 @@ def test_npy_cache_streams_to_device(gold_si, tmp_path):
         E._UPLOAD_CHUNK_BYTES = old
     b = calc.calculate(np.zeros(len(kv)), kv).sed
     np.testing.assert_array_equal(a, b)
+
+
+# ------------------------------------------------------------------ BASELINE configs at FULL size, k-subset vs the oracle
+def _subset_parity(calc, traj, kv_sub, **kw):
+    """new / O-ref / O-64 on a handful of k-points of a full-size trajectory (the oracle's cost is linear in k)."""
+    new = calc.calculate(np.zeros(len(kv_sub), np.float32), kv_sub, **kw)
+    ref = O.calculate(traj.positions, traj.velocities, traj.types, traj.dt_ps, kv_sub, **kw)
+    o64 = O.calculate_fp64(traj.positions, traj.velocities, traj.types, traj.dt_ps, kv_sub, **kw)
+    assert new.sed.shape == ref["sed"].shape and new.sed.dtype == ref["sed"].dtype
+    assert new.is_complex == ref["is_complex"]
+    if new.is_complex:
+        i_new, i_ref = O.intensity(new.sed).astype(np.float64), O.intensity(ref["sed"]).astype(np.float64)
+        i_64 = np.sum(np.abs(o64["sed"]) ** 2, axis=-1)
+    else:
+        i_new, i_ref, i_64 = new.sed.astype(np.float64), ref["sed"].astype(np.float64), o64["sed"]
+    rep = O.parity_report(i_new, i_ref, i_64)
+    print({t: {k: f"{v['max']:.2e}" for k, v in rep[t].items()} for t in (1e-4, 1e-5, 1e-6)})
+    assert rep["global_peak_equal"] and rep["per_k_peak_equal"]
+    assert rep[1e-6]["new_o64"]["max"] < 1e-5                      # north-star tolerance against the truth
+    # ... and at the level of the reference's own rounding floor (both are a few 1e-6 at these sizes)
+    assert rep[1e-6]["new_o64"]["max"] <= max(1.5 * rep[1e-6]["ref_o64"]["max"], 4e-6)
+    assert rep[1e-6]["new_ref"]["max"] < max(1e-5, 1.3 * rep[1e-6]["ref_o64"]["max"])
+    assert rep[1e-4]["new_ref"]["max"] < 1e-5
+    return new, rep
+
+
+@pytest.mark.parametrize("name", ["c1", "c2"])
+def test_full_size_baseline_config_parity_on_k_subset(name):
+    from psa_b200 import SEDCalculator
+    cfg = synth.baseline_config(name)
+    spec = cfg["spec"]
+    traj = spec.trajectory()
+    calc = SEDCalculator(traj, *spec.cells)
+    path = cfg["paths"][0]
+    mags, kv = calc.get_k_path(path["direction"], cfg["bz_coverage"], path["n_k"])
+    # the dispersion-peak column, its neighbours and a few others
+    full = calc.calculate(mags, kv, basis_atom_types=cfg["basis_atom_types"], summation_mode=cfg["summation_mode"])
+    inten = full.intensity if full.is_complex else full.sed
+    k_pk = int(np.unravel_index(np.argmax(inten), inten.shape)[1])
+    pick = sorted({0, 1, max(k_pk - 1, 0), k_pk, min(k_pk + 1, len(kv) - 1), len(kv) // 2, len(kv) - 1})
+    new, _ = _subset_parity(calc, traj, kv[pick], basis_atom_types=cfg["basis_atom_types"],
+                            summation_mode=cfg["summation_mode"])
+    # the subset call and the full call agree bit for bit (k columns are independent and exact)
+    np.testing.assert_array_equal(new.sed, full.sed[:, pick])
+
+
+def test_full_size_graphene_chirality():
+    """C3 at full size: parity on a k-subset, and the handedness of the planted circular modes."""
+    from psa_b200 import SEDCalculator
+    cfg = synth.baseline_config("c3")
+    spec = cfg["spec"]
+    traj = spec.trajectory()
+    calc = SEDCalculator(traj, *spec.cells)
+    res = calc.calculate_chiral_sed([1, 0, 0], cfg["bz_coverage"], 80, chiral_axis="z")
+    assert res.phase.shape == res.sed.shape[:2] and np.abs(res.phase).max() <= np.pi / 2 + 1e-6
+    _subset_parity(calc, traj, res.k_vectors[[0, 7, 20, 41, 79]], summation_mode="coherent")
+    # A planted mode u = A Re[(x + i h y)/sqrt2 e^{i(q.r - w t)}] shows up at (k, f) = (+q, +w) through its
+    # conjugate term, S_y / S_x = -i h, and at (-q, -w) with S_y / S_x = +i h: the folded phase
+    # arg(S_x) - arg(S_y) must be +h pi/2 resp. -h pi/2 there.  Modes whose q lies on the sampled [100] path
+    # are checked at the nearest k sample, at the exact frequency bin.
+    df = 1.0 / (spec.n_frames * spec.dt_ps)
+    on_bin = [(q, f, np.sign(h)) for q, f, h in zip(spec.q, spec.freq, spec.pol_im[:, 1])
+              if abs(q[1]) < 1e-9 and abs(q[2]) < 1e-9 and q[0] > 0 and abs(f / df - round(f / df)) < 1e-6]
+    assert on_bin, "the synthetic graphene spec must plant at least one on-bin mode along [100]"
+    kq = np.array([[q[0], 0.0, 0.0] for q, _, _ in on_bin], np.float32)          # sample exactly at the planted q
+    at_q = calc.calculate(np.zeros(len(kq), np.float32), kq)
+    phase = calc.calculate_chiral_phase(at_q.sed[:, :, 0], at_q.sed[:, :, 1], "C")
+    inten = O.intensity(at_q.sed)
+    for col, (q, f, h) in enumerate(on_bin):
+        f_bin = int(round(f / df))
+        assert inten[f_bin, col] > 0.2 * inten[:, col].max()                         # the planted line is there
+        assert abs(phase[f_bin, col] - h * np.pi / 2) < 0.1, (q, f, h, phase[f_bin, col])
