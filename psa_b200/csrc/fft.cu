@@ -38,7 +38,14 @@
 
 namespace psa {
 
-constexpr int kFftThreads = 512;
+#ifndef PSA_FFT_THREADS
+#define PSA_FFT_THREADS 512
+#endif
+#ifndef PSA_FFT_UNROLL
+#define PSA_FFT_UNROLL 2
+#endif
+constexpr int kFftThreads = PSA_FFT_THREADS;
+constexpr int kFftUnroll = PSA_FFT_UNROLL;
 constexpr int64_t kMaxSmemPoints = 16384;   // complex64 points that fit one CTA (128 KiB + padding)
 constexpr int64_t kMaxTransform = (int64_t)1 << 20;
 constexpr int kBlk = 16;                    // points finished in registers per thread
@@ -123,7 +130,7 @@ struct FftGeom {
 template <int RADIX>
 __device__ __forceinline__ void smem_pass(float2* __restrict__ s, int m, int L, const double2* __restrict__ tab) {
   const int q = L / RADIX;
-#pragma unroll 2
+#pragma unroll kFftUnroll
   for (int b = threadIdx.x; b < m / RADIX; b += blockDim.x) {
     const int j = b & (q - 1);
     const int base = (b - j) * RADIX + j;            // (b / q) * L + j

@@ -11,32 +11,42 @@ namespace psa {
 // SURVEY.md appendix A).
 // ---------------------------------------------------------------------------------------------
 // The adds of one column are inherently serial, so bandwidth has to come from memory-level
-// parallelism instead: a CTA owns 32 adjacent columns (one 128-byte line per frame); all 16 warps
-// stream a tile of 256 frames into registers (16 independent coalesced loads per thread, issued
-// while the previous tile is being consumed), park it in shared memory, and warp 0 then performs
-// the ordered float32 additions from shared memory.
-constexpr int kMeanCols = 32;
-constexpr int kMeanRows = 256;
+// parallelism instead: a CTA owns kMeanCols adjacent columns; all 16 warps stream a tile of kMeanRows
+// frames into registers (independent coalesced loads, issued while the previous tile is being
+// consumed), park it in shared memory, and one warp per 32 columns then performs the ordered float32
+// additions from shared memory.
+#ifndef PSA_MEAN_COLS
+#define PSA_MEAN_COLS 32
+#endif
+#ifndef PSA_MEAN_ROWS
+#define PSA_MEAN_ROWS 256
+#endif
+constexpr int kMeanCols = PSA_MEAN_COLS;        // columns per CTA (multiple of 32): one consumer warp per 32
+constexpr int kMeanRows = PSA_MEAN_ROWS;        // frames per tile
 constexpr int kMeanThreads = 512;
-constexpr int kMeanPerThread = kMeanRows / (kMeanThreads / 32);   // 16 rows per thread per tile
+constexpr int kMeanPerThread = kMeanRows * kMeanCols / kMeanThreads;   // loads in flight per thread
+constexpr int kMeanConsumers = kMeanCols / 32;
 
 __global__ void __launch_bounds__(kMeanThreads) mean_positions_kernel(const float* __restrict__ pos, int64_t n_t,
                                                                       int64_t n_cols, float* __restrict__ mean) {
   extern __shared__ float mean_smem[];
   float (*tile)[kMeanRows][kMeanCols] = reinterpret_cast<float (*)[kMeanRows][kMeanCols]>(mean_smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t col = (int64_t)blockIdx.x * kMeanCols + lane;
-  const bool col_ok = col < n_cols;
-  const float* p = pos + col;
+  const int64_t col0 = (int64_t)blockIdx.x * kMeanCols;
   const int64_t n_tiles = (n_t + kMeanRows - 1) / kMeanRows;
+  // element e = threadIdx.x + i * kMeanThreads of a tile: row e / kMeanCols, column e % kMeanCols
+  const int my_col = threadIdx.x % kMeanCols, my_row0 = threadIdx.x / kMeanCols;
+  constexpr int kRowStep = kMeanThreads / kMeanCols;
+  const bool load_ok = col0 + my_col < n_cols;
+  const float* p = pos + col0 + my_col;
 
   float v[kMeanPerThread];
   auto fetch = [&](int64_t tile_idx) {
-    const int64_t t0 = tile_idx * kMeanRows + warp;
+    const int64_t t0 = tile_idx * kMeanRows + my_row0;
 #pragma unroll
     for (int i = 0; i < kMeanPerThread; ++i) {
-      const int64_t t = t0 + (int64_t)i * (kMeanThreads / 32);
-      v[i] = (col_ok && t < n_t) ? __ldg(p + t * n_cols) : 0.0f;
+      const int64_t t = t0 + (int64_t)i * kRowStep;
+      v[i] = (load_ok && t < n_t) ? __ldg(p + t * n_cols) : 0.0f;
     }
   };
 
@@ -45,22 +55,26 @@ __global__ void __launch_bounds__(kMeanThreads) mean_positions_kernel(const floa
   for (int64_t it = 0; it < n_tiles; ++it) {
     const int buf = (int)(it & 1);
 #pragma unroll
-    for (int i = 0; i < kMeanPerThread; ++i) tile[buf][warp + i * (kMeanThreads / 32)][lane] = v[i];
+    for (int i = 0; i < kMeanPerThread; ++i) tile[buf][my_row0 + i * kRowStep][my_col] = v[i];
     __syncthreads();
-    if (it + 1 < n_tiles) fetch(it + 1);              // in flight while warp 0 consumes this tile
-    if (warp == 0) {
+    if (it + 1 < n_tiles) fetch(it + 1);              // in flight while the consumer warps add this tile
+    if (warp < kMeanConsumers) {
+      const int c = warp * 32 + lane;
       const int64_t rows = (n_t - it * kMeanRows) < kMeanRows ? (n_t - it * kMeanRows) : kMeanRows;
       if (rows == kMeanRows) {
 #pragma unroll 16
-        for (int r = 0; r < kMeanRows; ++r) acc = __fadd_rn(acc, tile[buf][r][lane]);
+        for (int r = 0; r < kMeanRows; ++r) acc = __fadd_rn(acc, tile[buf][r][c]);
       } else {
-        for (int r = 0; r < (int)rows; ++r) acc = __fadd_rn(acc, tile[buf][r][lane]);
+        for (int r = 0; r < (int)rows; ++r) acc = __fadd_rn(acc, tile[buf][r][c]);
       }
     }
     // the store into tile[buf] two iterations from now is ordered after this read by the
     // __syncthreads of the next iteration
   }
-  if (warp == 0 && col_ok) mean[col] = __fdiv_rn(acc, (float)n_t);
+  if (warp < kMeanConsumers) {
+    const int64_t col = col0 + warp * 32 + lane;
+    if (col < n_cols) mean[col] = __fdiv_rn(acc, (float)n_t);
+  }
 }
 
 int launch_mean_positions(const float* pos, int64_t n_t, int64_t n_a, float* mean, cudaStream_t s) {
