@@ -13,7 +13,7 @@
 //                                            on the LEADER's full barrier (peer bit cleared)
 //   MMA issuer (warp 1 lane 0 of the leader) tcgen05.mma.cta_group::2 M256; tcgen05.commit multicast
 //                                            to both CTAs' empty / tmem_full barriers
-//   epilogue (warps 2..9 of BOTH CTAs)       drain their own TMEM half, then arrive on the leader's
+//   epilogue (warps 2..17 of BOTH CTAs)      drain their own TMEM half, then arrive on the leader's
 //                                            tmem_empty barrier (remote arrive from rank 1)
 #include <cuda.h>
 
@@ -35,7 +35,11 @@ constexpr int B_BYTES = kSlices * B_SLICE_BYTES;         // 16 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;           // 48 KiB
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
-constexpr int EPI_WARPS = 8;
+#ifndef PSA_EPI_WARPS
+#define PSA_EPI_WARPS 16
+#endif
+constexpr int EPI_WARPS = PSA_EPI_WARPS;      // 4 TMEM lane quarters x (EPI_WARPS / 4) column parts
+constexpr int EPI_COLS = BN / (EPI_WARPS / 4); // columns of each class drained by one warp
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;            // shared::cluster address of the same offset in the even CTA
@@ -256,9 +260,9 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tmap_phase, const __grid_
         tile_phase ^= 1;
       }
     }
-  } else {                                                     // ---------------- epilogue warps 2..9 (both CTAs)
+  } else {                                                     // ---------------- epilogue warps 2..17 (both CTAs)
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;
     uint32_t tile_phase = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
       const TileCoord tc = decode_tile(tile, r_tiles, t_tiles, rows);
@@ -268,9 +272,9 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tmap_phase, const __grid_
       const bool t_ok = t < n_t;
       const int e = t_ok ? __ldg(expo + (int64_t)tc.pol * n_t + t) : kExpMin;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      const int c_end = min(tc.n_cols, half * 64 + 64);
+      const int c_end = min(tc.n_cols, part * EPI_COLS + EPI_COLS);
 #pragma unroll 1
-      for (int c0 = half * 64; c0 < c_end; c0 += 16) {
+      for (int c0 = part * EPI_COLS; c0 < c_end; c0 += 16) {
         uint32_t r0[16], r1[16], r2[16], r3[16];
         PSA_TMEM_LD16(r0, lane_addr + 0 * BN + c0);
         PSA_TMEM_LD16(r1, lane_addr + 1 * BN + c0);
