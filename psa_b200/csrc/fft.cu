@@ -95,8 +95,10 @@ __device__ __forceinline__ void bfly8(cd (&a)[8]) {
 // the power-of-two core
 // ---------------------------------------------------------------------------------------------
 // Pass schedule for an m = 2^log2m point sub-transform and the layout of its per-pass twiddle tables:
-// pass p has span L[p], radix r[p], q = L/r butterflies per block, and (r-1)*q table entries
-// w_L^{i j} (i = 1..r-1 major, j < q minor) starting at tw_off[p].
+// pass p has span L[p], radix r[p], q = L/r butterflies per block, and q table entries w_L^j (j < q)
+// starting at tw_off[p]; the higher powers w_L^{2j} .. w_L^{(r-1)j} are formed in float64 registers
+// (six complex products for radix 8) instead of being loaded - the pass is bound by load latency,
+// not by the FP64 pipe.
 struct PassPlan {
   int n_pass, total;
   int L[kMaxPasses], r[kMaxPasses], tw_off[kMaxPasses];
@@ -105,7 +107,7 @@ __host__ __device__ inline void plan_add(PassPlan& pp, int L, int r) {
   pp.L[pp.n_pass] = L;
   pp.r[pp.n_pass] = r;
   pp.tw_off[pp.n_pass] = pp.total;
-  pp.total += (r - 1) * (L / r);
+  pp.total += L / r;
   ++pp.n_pass;
 }
 __host__ __device__ inline PassPlan make_passes(int log2m) {
@@ -128,31 +130,65 @@ struct FftGeom {
 };
 
 template <int RADIX>
+__device__ __forceinline__ void smem_butterfly(float2* __restrict__ s, int b, int q, int qs,
+                                               const double2* __restrict__ tab) {
+  const int j = b & (q - 1);
+  const int p0 = phys((b - j) * RADIX + j);            // (b / q) * L + j
+  const double2 t = __ldg(tab + j);
+  cd a[RADIX];
+#pragma unroll
+  for (int i = 0; i < RADIX; ++i) a[i] = widen(s[p0 + i * qs]);
+  const cd w1 = mk(t.x, t.y);
+  if (RADIX == 2) {
+    bfly2(a[0], a[1]);
+    a[1] = cmul(a[1], w1);
+  }
+  if (RADIX == 4) {
+    bfly4(a[0], a[1], a[2], a[3]);
+    const cd w2 = cmul(w1, w1);
+    a[1] = cmul(a[1], w1);
+    a[2] = cmul(a[2], w2);
+    a[3] = cmul(a[3], cmul(w2, w1));
+  }
+  if (RADIX == 8) {
+    bfly8(reinterpret_cast<cd(&)[8]>(a));
+    const cd w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
+    a[1] = cmul(a[1], w1);
+    a[2] = cmul(a[2], w2);
+    a[3] = cmul(a[3], w3);
+    a[4] = cmul(a[4], w4);
+    a[5] = cmul(a[5], cmul(w4, w1));
+    a[6] = cmul(a[6], cmul(w3, w3));
+    a[7] = cmul(a[7], cmul(w4, w3));
+  }
+#pragma unroll
+  for (int i = 0; i < RADIX; ++i) s[p0 + i * qs] = narrow(a[i]);
+}
+
+template <int RADIX>
 __device__ __forceinline__ void smem_pass(float2* __restrict__ s, int m, int L, const double2* __restrict__ tab) {
   const int q = L / RADIX;
+  const int qs = q + (q >> 4);                         // leg stride in padded storage (q is a multiple of 16)
+  const int n_bfly = m / RADIX, step = blockDim.x;
+  if (n_bfly % step == 0) {                            // uniform trip count: no exit test between iterations
+    const int per_thread = n_bfly / step;
 #pragma unroll kFftUnroll
-  for (int b = threadIdx.x; b < m / RADIX; b += blockDim.x) {
-    const int j = b & (q - 1);
-    const int base = (b - j) * RADIX + j;            // (b / q) * L + j
-    cd a[RADIX];
-#pragma unroll
-    for (int i = 0; i < RADIX; ++i) a[i] = widen(s[phys(base + i * q)]);
-    if (RADIX == 2) bfly2(a[0], a[1]);
-    if (RADIX == 4) bfly4(a[0], a[1], a[2], a[3]);
-    if (RADIX == 8) bfly8(reinterpret_cast<cd(&)[8]>(a));
-    s[phys(base)] = narrow(a[0]);
-#pragma unroll
-    for (int i = 1; i < RADIX; ++i) s[phys(base + i * q)] = narrow(cmul(a[i], __ldg(tab + (i - 1) * q + j)));
+    for (int i = 0; i < per_thread; ++i) smem_butterfly<RADIX>(s, threadIdx.x + i * step, q, qs, tab);
+  } else {
+    for (int b = threadIdx.x; b < n_bfly; b += step) smem_butterfly<RADIX>(s, b, q, qs, tab);
   }
   __syncthreads();
 }
 
 __device__ void fft_smem_passes(float2* __restrict__ s, const FftGeom& g) {
-  for (int p = 0; p < g.pp.n_pass; ++p) {
-    const double2* tab = g.pass_tw + g.pp.tw_off[p];
-    if (g.pp.r[p] == 8) smem_pass<8>(s, g.m, g.pp.L[p], tab);
-    else if (g.pp.r[p] == 4) smem_pass<4>(s, g.m, g.pp.L[p], tab);
-    else smem_pass<2>(s, g.m, g.pp.L[p], tab);
+#pragma unroll                                           // static indices keep the plan in the constant bank
+  for (int p = 0; p < kMaxPasses; ++p) {
+    if (p < g.pp.n_pass) {
+      const double2* tab = g.pass_tw + g.pp.tw_off[p];
+      if (g.pp.r[p] == 8) smem_pass<8>(s, g.m, g.pp.L[p], tab);
+      else if (g.pp.r[p] == 4) smem_pass<4>(s, g.m, g.pp.L[p], tab);
+      else smem_pass<2>(s, g.m, g.pp.L[p], tab);
+    }
   }
 }
 
@@ -189,11 +225,14 @@ __device__ __forceinline__ void fft16_registers(cd (&x)[kBlk]) {
 __device__ __forceinline__ int block_base_frequency(int b, const FftGeom& g) {
   int bits = g.log2m - 4;      // bits of the block index, consumed most-significant first, one digit per pass
   int f = 0, shift = 0;
-  for (int p = 0; p < g.pp.n_pass; ++p) {
-    const int w = g.pp.r[p] == 8 ? 3 : (g.pp.r[p] == 4 ? 2 : 1);
-    bits -= w;
-    f += ((b >> bits) & (g.pp.r[p] - 1)) << shift;
-    shift += w;
+#pragma unroll
+  for (int p = 0; p < kMaxPasses; ++p) {
+    if (p < g.pp.n_pass) {
+      const int w = g.pp.r[p] == 8 ? 3 : (g.pp.r[p] == 4 ? 2 : 1);
+      bits -= w;
+      f += ((b >> bits) & (g.pp.r[p] - 1)) << shift;
+      shift += w;
+    }
   }
   return f;
 }
@@ -202,8 +241,39 @@ __device__ __forceinline__ int block_base_frequency(int b, const FftGeom& g) {
 template <class Fetch>
 __device__ void load_column(float2* __restrict__ s, const Fetch& fetch, const FftGeom& g, int r) {
   if (g.R == 1) {
-#pragma unroll 4
-    for (int t = threadIdx.x; t < g.m; t += blockDim.x) s[phys(t)] = narrow(fetch(t));
+    // Latency-bound: every thread first issues the loads of 16 elements (32 loads in flight), then parks
+    // them in shared memory.  A plain strided loop keeps an exit test between unrolled iterations, which
+    // serialises load -> store (ncu: 1/3 of all stall samples sat on that store).
+    const int step = blockDim.x;
+    int t = threadIdx.x;
+    for (; t + 15 * step < g.m; t += 16 * step) {
+      float2 v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = narrow(fetch(t + u * step));
+#pragma unroll
+      for (int u = 0; u < 16; ++u) s[phys(t + u * step)] = v[u];
+    }
+    for (; t < g.m; t += step) s[phys(t)] = narrow(fetch(t));
+    return;
+  }
+  if (g.R == 2) {                                     // 16385 .. 32768 points: x[t] +- x[t + m], batched like above
+    const int step = blockDim.x;
+    int t = threadIdx.x;
+    for (; t + 7 * step < g.m; t += 8 * step) {
+      cd a[8], b[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        a[u] = fetch(t + u * step);
+        b[u] = fetch(t + u * step + g.m);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        s[phys(t + u * step)] = narrow(r ? cmul(csub(a[u], b[u]), __ldg(g.tw + t + u * step)) : cadd(a[u], b[u]));
+    }
+    for (; t < g.m; t += step) {
+      cd a = fetch(t), b = fetch(t + g.m);
+      s[phys(t)] = narrow(r ? cmul(csub(a, b), __ldg(g.tw + t)) : cadd(a, b));
+    }
     return;
   }
   for (int t = threadIdx.x; t < g.m; t += blockDim.x) {
@@ -475,12 +545,11 @@ __global__ void twiddle_kernel(int64_t n, double2* __restrict__ tw) {
 
 __global__ void pass_table_kernel(int L, int radix, double2* __restrict__ table) {   // table already offset to the pass
   const int q = L / radix;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (radix - 1) * q) return;
-  const int leg = i / q + 1, j = i % q;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= q) return;
   double s, c;
-  sincospi(2.0 * (double)((leg * j) % L) / (double)L, &s, &c);
-  table[i] = make_double2(c, -s);
+  sincospi(2.0 * (double)j / (double)L, &s, &c);
+  table[j] = make_double2(c, -s);
 }
 
 // chirp[t] = exp(+i pi t^2 / n) with t^2 reduced mod 2n in integers; padded[] = the circular kernel of length M
@@ -557,7 +626,7 @@ static int build_tables(int64_t n_fft, double2* tw, cudaStream_t s) {
   const PassPlan pp = make_passes(ilog2(sub_length(n_fft, nullptr)));
   double2* pass = tw + n_fft;
   for (int p = 0; p < pp.n_pass; ++p) {
-    const int entries = (pp.r[p] - 1) * (pp.L[p] / pp.r[p]);
+    const int entries = pp.L[p] / pp.r[p];
     pass_table_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, s>>>(pp.L[p], pp.r[p], pass + pp.tw_off[p]);
   }
   return launch_status("fft table kernels");

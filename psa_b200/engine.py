@@ -55,6 +55,13 @@ class Engine:
     def empty(self, shape, dtype) -> torch.Tensor:
         return torch.empty(shape, dtype=dtype, device=self.device)
 
+    def upload_small(self, arr: np.ndarray) -> torch.Tensor:
+        """Stream-ordered upload of a small host array.  A plain ``tensor.to(device)`` from pageable memory
+        blocks the host until everything queued on the stream has finished (measured: 0.35 ms per call
+        inside a 1 ms step); staging through pinned memory keeps the host running ahead of the GPU."""
+        staged = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+        return staged.to(self.device, non_blocking=True)
+
     def _run(self, kernel: str, n_launches: int, *args) -> None:
         """One C-ABI call; with ``self.profile`` set, bracketed by CUDA events on the launching stream."""
         self.launches += n_launches
@@ -156,6 +163,7 @@ class DeviceTrajectory:
         self._dev: Dict[str, torch.Tensor] = {}
         self._mean: Optional[torch.Tensor] = None
         self._groups: Dict[Tuple, Tuple] = {}
+        self._indices: Dict[Optional[str], torch.Tensor] = {}
         self._lock = threading.RLock()
         self.h2d_bytes = 0
 
@@ -224,6 +232,13 @@ class DeviceTrajectory:
                                                           digest_size=16).hexdigest()
         return (use_displacements, digest), idx
 
+    def _index_tensor(self, key: Tuple, idx: np.ndarray) -> torch.Tensor:
+        """Device copy of an atom index list; survives ``reset_derived`` (it does not depend on the data)."""
+        hit = self._indices.get(key[1])
+        if hit is None:
+            hit = self._indices[key[1]] = self.engine.upload_small(np.ascontiguousarray(idx, np.int32))
+        return hit
+
     def install_mean(self, mean: torch.Tensor) -> None:
         """Adopt mean positions computed elsewhere (multi-GPU: broadcast from the source rank)."""
         with self._lock:
@@ -233,7 +248,7 @@ class DeviceTrajectory:
                       expo: torch.Tensor) -> None:
         """Adopt digit planes computed elsewhere for the atom selection ``idx``."""
         key, idx = self._group_key(idx, use_displacements)
-        idx_dev = None if idx is None else torch.from_numpy(np.ascontiguousarray(idx, np.int32)).to(self.engine.device)
+        idx_dev = None if idx is None else self._index_tensor(key, idx)
         n_sel = self.n_a if idx is None else int(idx.size)
         with self._lock:
             self._groups[key] = (idx_dev, n_sel, int(dig.shape[-1]), dig, expo)
@@ -256,7 +271,7 @@ class DeviceTrajectory:
             if idx is None:
                 idx_dev, n_sel = None, self.n_a
             else:
-                idx_dev = torch.from_numpy(np.ascontiguousarray(idx, np.int32)).to(eng.device)
+                idx_dev = self._index_tensor(key, idx)
                 n_sel = int(idx.size)
             if use_displacements:
                 dig, expo, pitch = eng.digitize(self.positions, self.mean, idx_dev, n_sel)
@@ -287,7 +302,7 @@ def sed_on_device(traj: DeviceTrajectory, k_vecs: np.ndarray, groups: Sequence[O
     kc = max(1, min(k_chunk, n_k, K_CHUNK_CAP))
     rows_alloc = 2 * kc
     ldp = (n_t + 3) // 4 * 4
-    kv_dev = torch.from_numpy(np.ascontiguousarray(k_vecs, np.float32)).to(eng.device)
+    kv_dev = eng.upload_small(np.ascontiguousarray(k_vecs, np.float32))
     P = eng.empty((len(entries), rows_alloc, 3, ldp), torch.float32)
     group_stride = rows_alloc * 3 * ldp
     adig_bufs: Dict[int, torch.Tensor] = {}
