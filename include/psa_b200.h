@@ -120,6 +120,12 @@ int psa_disp_moments(const float* pos, const float* mean, const int32_t* idx, in
 /* max |x| over n float32 values (device scalar out). */
 int psa_absmax(const float* x, int64_t n, float* out, void* stream);
 
+/* Strided row copy between any two of {device, pinned host}: `height` rows of `width` bytes, row pitches in
+ * bytes.  Used to stream the spectra of one k-chunk into its column slice of the host result
+ * full_sed_data[:, k0:k1, :] (reference: sed_calculator.py:310, 325) while the next chunk is computed. */
+int psa_copy_rows(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width, int64_t height,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,7 +27,7 @@ from . import groups as grp
 from . import kspace
 from .directions import parse_direction
 from .dump import write_lammps_dump
-from .engine import DeviceTrajectory, Engine, sed_on_device
+from .engine import K_CHUNK_CAP, DeviceTrajectory, Engine, sed_on_device
 from .sed import SED
 from .trajectory import Trajectory
 
@@ -123,23 +123,34 @@ class SEDCalculator:
             return SED(np.array([], dtype=np.complex64).reshape(0, 0, 3), np.array([], dtype=np.float32),
                        k_points_mags, k_vectors_3d, k_grid_shape=k_grid_shape, is_complex=True, phase=None)
 
-        out_dev, complex_out, groups = self._calculate_device(k_vectors_3d, basis_atom_indices, basis_atom_types,
-                                                              summation_mode, k_chunk_size)
-        sed_host = self._to_host(out_dev)
+        sed_host, complex_out, groups = self._calculate_device(k_vectors_3d, basis_atom_indices, basis_atom_types,
+                                                               summation_mode, k_chunk_size, to_host=True)
         freqs = np.fft.fftfreq(n_t, d=self.dt_ps)
         return SED(sed_host, freqs, k_points_mags, k_vectors_3d, k_grid_shape=k_grid_shape,
                    is_complex=complex_out, phase=None, context=self._context(groups))
 
-    def _calculate_device(self, k_vectors_3d, basis_atom_indices, basis_atom_types, summation_mode, k_chunk_size=500):
-        """Device-resident result of ``calculate`` (what ``bench.py`` times as the kernel-only path)."""
+    def _calculate_device(self, k_vectors_3d, basis_atom_indices, basis_atom_types, summation_mode, k_chunk_size=500,
+                          to_host: bool = False):
+        """Device-resident result of ``calculate`` (what ``bench.py`` times as the kernel-only path), or with
+        ``to_host`` the host array.  A k-set longer than one chunk is streamed: each chunk's spectra go to
+        pinned host memory while the next chunk is computed, and nothing result-sized stays on the device."""
         groups = grp.resolve_sed_groups(self.traj.types, self.traj.n_atoms, basis_atom_indices,
                                         basis_atom_types, summation_mode)
         complex_out, proj_groups = grp.plan_sed_groups(groups, summation_mode)
         k_vecs = np.ascontiguousarray(np.asarray(k_vectors_3d, dtype=np.float32).reshape(-1, 3))
+        k_chunk = max(1, int(k_chunk_size))
+        n_t, n_k = self.traj.n_frames, k_vecs.shape[0]
         with torch.cuda.device(self.engine.device):
+            if to_host and n_k > min(k_chunk, K_CHUNK_CAP):
+                host = torch.empty((n_t, n_k, 3) if complex_out else (n_t, n_k),
+                                   dtype=torch.complex64 if complex_out else torch.float32, pin_memory=True)
+                sed_on_device(self.device_trajectory, k_vecs, proj_groups, complex_out, self.use_displacements,
+                              k_chunk=k_chunk, host_out=host)
+                self.engine.copy_stream.synchronize()
+                return host.numpy(), complex_out, groups
             out = sed_on_device(self.device_trajectory, k_vecs, proj_groups, complex_out,
-                                self.use_displacements, k_chunk=max(1, int(k_chunk_size)))
-        return out, complex_out, groups
+                                self.use_displacements, k_chunk=k_chunk)
+            return (self._to_host(out) if to_host else out), complex_out, groups
 
     def _to_host(self, dev: torch.Tensor) -> np.ndarray:
         host = torch.empty(dev.shape, dtype=dev.dtype, pin_memory=True)

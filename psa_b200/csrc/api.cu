@@ -147,4 +147,16 @@ int psa_absmax(const float* x, int64_t n, float* out, void* stream) {
   return launch_absmax(x, n, out, as_stream(stream));
 }
 
+int psa_copy_rows(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width, int64_t height,
+                  void* stream) {
+  if (width == 0 || height == 0) return PSA_OK;
+  PSA_REQUIRE(dst && src, "psa_copy_rows: null pointer");
+  PSA_REQUIRE(width > 0 && height > 0 && dst_pitch >= width && src_pitch >= width,
+              "psa_copy_rows: bad extent (width=%lld height=%lld pitches %lld / %lld)", (long long)width,
+              (long long)height, (long long)dst_pitch, (long long)src_pitch);
+  PSA_CUDA(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)width, (size_t)height,
+                             cudaMemcpyDefault, as_stream(stream)));
+  return PSA_OK;
+}
+
 }  // extern "C"

@@ -7,10 +7,12 @@
 //
 // Precision.  NumPy's complex64 FFT (the reference, sed_calculator.py:83) is accurate to a single
 // float32 rounding (measured rms error 2e-8), far better than a transform whose every butterfly
-// rounds to float32 (1e-7, scripts/fft_accuracy.py).  To stay at the reference's level the column is
-// STORED as float32 in shared memory but every butterfly is evaluated in float64 registers with
-// float64 twiddles, so a value is rounded once per shared-memory pass (at most 5 times) instead of
-// once per butterfly level.  The FP64 pipe is otherwise idle and the kernel is not bound by it.
+// rounds to float32 (1e-7, scripts/fft_accuracy.py).  To stay at the reference's level the whole
+// transform is carried in float64: float64 shared-memory storage, float64 butterflies and twiddles,
+// and ONE rounding to float32 when the spectrum is stored (scripts/fft_accuracy.py: the rms error
+// equals NumPy's at every length).  B200 runs FP64 at half the FP32 rate, so this costs little; the
+// float32 <-> float64 conversions (16-lane XU pipe) are confined to the load and the final store.
+// -DPSA_FFT_STORE64=0 rebuilds the earlier float32-storage variant (rounds once per pass) for A/B runs.
 //
 // Power-of-two core (forward, decimation in frequency, in place, m = 2^s points, 16 <= m <= 16384):
 //   * shared-memory passes of radix 8 (one leading radix-2 or radix-4 pass when (s-4) % 3 != 0) down
@@ -20,9 +22,10 @@
 //     radix 4 x 4 and hands the 16 results (digit-reversed frequency index) to a sink.  The array is
 //     padded by one element per 16 (index p lives at p + p/16), which makes these per-thread
 //     contiguous reads conflict-free as well.
-//   * transforms longer than 16384 points do not fit one CTA's shared memory: they are split by a
-//     radix-R decimation-in-frequency step applied while loading, giving R independent
-//     sub-transforms that produce the frequencies f = R f' + r.
+//   * a CTA transforms at most 4096 points (68 KiB of float64 storage, three CTAs per SM).  Longer
+//     columns are split by a radix-R decimation-in-frequency step applied while loading, giving R
+//     independent sub-transforms (one CTA each) that produce the frequencies f = R f' + r; the R
+//     CTAs of a column run side by side and share its samples through L2.
 //   * twiddles: float64 tables, per pass and contiguous in the butterfly index (a warp reads short
 //     contiguous runs), plus w_n^j for the load-time split.
 //
@@ -38,21 +41,34 @@
 
 namespace psa {
 
+#ifndef PSA_FFT_STORE64
+#define PSA_FFT_STORE64 1
+#endif
 #ifndef PSA_FFT_THREADS
-#define PSA_FFT_THREADS 512
+#define PSA_FFT_THREADS (PSA_FFT_STORE64 ? 256 : 512)
 #endif
 #ifndef PSA_FFT_UNROLL
 #define PSA_FFT_UNROLL 2
 #endif
+#ifndef PSA_FFT_MIN_CTAS
+#define PSA_FFT_MIN_CTAS (PSA_FFT_STORE64 ? 3 : 1)
+#endif
 constexpr int kFftThreads = PSA_FFT_THREADS;
 constexpr int kFftUnroll = PSA_FFT_UNROLL;
-constexpr int64_t kMaxSmemPoints = 16384;   // complex64 points that fit one CTA (128 KiB + padding)
+constexpr int kFftMinCtas = PSA_FFT_MIN_CTAS;
+#if PSA_FFT_STORE64
+constexpr int64_t kMaxSmemPoints = 8192;       // complex128 points that fit one CTA (128 KiB + padding)
+constexpr int64_t kDefaultSmemPoints = 4096;   // 68 KiB: three CTAs per SM
+#else
+constexpr int64_t kMaxSmemPoints = 16384;      // complex64 points that fit one CTA (128 KiB + padding)
+constexpr int64_t kDefaultSmemPoints = 16384;
+#endif
 constexpr int64_t kMaxTransform = (int64_t)1 << 20;
 constexpr int kBlk = 16;                    // points finished in registers per thread
 constexpr int kMaxPasses = 5;
 
 // ---------------------------------------------------------------------------------------------
-// complex helpers (float64 arithmetic, float32 storage)
+// complex helpers (float64 arithmetic; sc = the shared-memory element)
 // ---------------------------------------------------------------------------------------------
 struct cd {
   double x, y;
@@ -60,6 +76,15 @@ struct cd {
 __device__ __forceinline__ cd mk(double x, double y) { cd r; r.x = x; r.y = y; return r; }
 __device__ __forceinline__ cd widen(float2 a) { return mk((double)a.x, (double)a.y); }
 __device__ __forceinline__ float2 narrow(cd a) { return make_float2((float)a.x, (float)a.y); }
+#if PSA_FFT_STORE64
+using sc = double2;
+__device__ __forceinline__ cd to_cd(sc a) { return mk(a.x, a.y); }
+__device__ __forceinline__ sc to_sc(cd a) { return make_double2(a.x, a.y); }
+#else
+using sc = float2;
+__device__ __forceinline__ cd to_cd(sc a) { return widen(a); }
+__device__ __forceinline__ sc to_sc(cd a) { return narrow(a); }
+#endif
 __device__ __forceinline__ cd cmul(cd a, cd b) { return mk(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x)); }
 __device__ __forceinline__ cd cmul(cd a, double2 b) { return mk(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x)); }
 __device__ __forceinline__ cd cmul_conj(cd a, cd b) { return mk(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -a.x * b.y)); }   // a conj(b)
@@ -130,14 +155,14 @@ struct FftGeom {
 };
 
 template <int RADIX>
-__device__ __forceinline__ void smem_butterfly(float2* __restrict__ s, int b, int q, int qs,
+__device__ __forceinline__ void smem_butterfly(sc* __restrict__ s, int b, int q, int qs,
                                                const double2* __restrict__ tab) {
   const int j = b & (q - 1);
   const int p0 = phys((b - j) * RADIX + j);            // (b / q) * L + j
   const double2 t = __ldg(tab + j);
   cd a[RADIX];
 #pragma unroll
-  for (int i = 0; i < RADIX; ++i) a[i] = widen(s[p0 + i * qs]);
+  for (int i = 0; i < RADIX; ++i) a[i] = to_cd(s[p0 + i * qs]);
   const cd w1 = mk(t.x, t.y);
   if (RADIX == 2) {
     bfly2(a[0], a[1]);
@@ -162,11 +187,11 @@ __device__ __forceinline__ void smem_butterfly(float2* __restrict__ s, int b, in
     a[7] = cmul(a[7], cmul(w4, w3));
   }
 #pragma unroll
-  for (int i = 0; i < RADIX; ++i) s[p0 + i * qs] = narrow(a[i]);
+  for (int i = 0; i < RADIX; ++i) s[p0 + i * qs] = to_sc(a[i]);
 }
 
 template <int RADIX>
-__device__ __forceinline__ void smem_pass(float2* __restrict__ s, int m, int L, const double2* __restrict__ tab) {
+__device__ __forceinline__ void smem_pass(sc* __restrict__ s, int m, int L, const double2* __restrict__ tab) {
   const int q = L / RADIX;
   const int qs = q + (q >> 4);                         // leg stride in padded storage (q is a multiple of 16)
   const int n_bfly = m / RADIX, step = blockDim.x;
@@ -180,7 +205,7 @@ __device__ __forceinline__ void smem_pass(float2* __restrict__ s, int m, int L, 
   __syncthreads();
 }
 
-__device__ void fft_smem_passes(float2* __restrict__ s, const FftGeom& g) {
+__device__ void fft_smem_passes(sc* __restrict__ s, const FftGeom& g) {
 #pragma unroll                                           // static indices keep the plan in the constant bank
   for (int p = 0; p < kMaxPasses; ++p) {
     if (p < g.pp.n_pass) {
@@ -237,27 +262,34 @@ __device__ __forceinline__ int block_base_frequency(int b, const FftGeom& g) {
   return f;
 }
 
+// output r of a 4-point forward DFT: sum_j x_j (-i)^{jr}
+__device__ __forceinline__ cd dif4(cd x0, cd x1, cd x2, cd x3, int r) {
+  if (r == 0) return cadd(cadd(x0, x2), cadd(x1, x3));
+  if (r == 2) return csub(cadd(x0, x2), cadd(x1, x3));
+  const cd d = mul_neg_i(csub(x1, x3));               // -i (x1 - x3)
+  return r == 1 ? cadd(csub(x0, x2), d) : csub(csub(x0, x2), d);
+}
+
 // Fill shared memory with sub-sequence r of the radix-R split of fetch(0..n_fft) (R == 1: plain copy).
 template <class Fetch>
-__device__ void load_column(float2* __restrict__ s, const Fetch& fetch, const FftGeom& g, int r) {
+__device__ void load_column(sc* __restrict__ s, const Fetch& fetch, const FftGeom& g, int r) {
+  const int step = blockDim.x;
   if (g.R == 1) {
     // Latency-bound: every thread first issues the loads of 16 elements (32 loads in flight), then parks
     // them in shared memory.  A plain strided loop keeps an exit test between unrolled iterations, which
     // serialises load -> store (ncu: 1/3 of all stall samples sat on that store).
-    const int step = blockDim.x;
     int t = threadIdx.x;
     for (; t + 15 * step < g.m; t += 16 * step) {
-      float2 v[16];
+      sc v[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) v[u] = narrow(fetch(t + u * step));
+      for (int u = 0; u < 16; ++u) v[u] = to_sc(fetch(t + u * step));
 #pragma unroll
       for (int u = 0; u < 16; ++u) s[phys(t + u * step)] = v[u];
     }
-    for (; t < g.m; t += step) s[phys(t)] = narrow(fetch(t));
+    for (; t < g.m; t += step) s[phys(t)] = to_sc(fetch(t));
     return;
   }
-  if (g.R == 2) {                                     // 16385 .. 32768 points: x[t] +- x[t + m], batched like above
-    const int step = blockDim.x;
+  if (g.R == 2) {                                     // x[t] +- x[t + m], batched like above
     int t = threadIdx.x;
     for (; t + 7 * step < g.m; t += 8 * step) {
       cd a[8], b[8];
@@ -268,35 +300,80 @@ __device__ void load_column(float2* __restrict__ s, const Fetch& fetch, const Ff
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u)
-        s[phys(t + u * step)] = narrow(r ? cmul(csub(a[u], b[u]), __ldg(g.tw + t + u * step)) : cadd(a[u], b[u]));
+        s[phys(t + u * step)] = to_sc(r ? cmul(csub(a[u], b[u]), __ldg(g.tw + t + u * step)) : cadd(a[u], b[u]));
     }
     for (; t < g.m; t += step) {
       cd a = fetch(t), b = fetch(t + g.m);
-      s[phys(t)] = narrow(r ? cmul(csub(a, b), __ldg(g.tw + t)) : cadd(a, b));
+      s[phys(t)] = to_sc(r ? cmul(csub(a, b), __ldg(g.tw + t)) : cadd(a, b));
     }
     return;
   }
-  for (int t = threadIdx.x; t < g.m; t += blockDim.x) {
+  if (g.R == 4) {                                     // sum_j x[t + j m] (-i)^{jr}, times w_n^{tr}
+    int t = threadIdx.x;
+    for (; t + 3 * step < g.m; t += 4 * step) {
+      cd x[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[u][j] = fetch(t + u * step + j * g.m);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const cd y = dif4(x[u][0], x[u][1], x[u][2], x[u][3], r);
+        s[phys(t + u * step)] = to_sc(r ? cmul(y, __ldg(g.tw + (t + u * step) * r)) : y);
+      }
+    }
+    for (; t < g.m; t += step) {
+      const cd y = dif4(fetch(t), fetch(t + g.m), fetch(t + 2 * g.m), fetch(t + 3 * g.m), r);
+      s[phys(t)] = to_sc(r ? cmul(y, __ldg(g.tw + t * r)) : y);
+    }
+    return;
+  }
+  if (g.R == 8) {                                     // even and odd j are radix-4 sums: E + w_8^r O
+    const double2 w8r = __ldg(g.tw + r * (g.n_fft >> 3));
+    int t = threadIdx.x;
+    for (; t + step < g.m; t += 2 * step) {
+      cd x[2][8];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[u][j] = fetch(t + u * step + j * g.m);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const cd y = cadd(dif4(x[u][0], x[u][2], x[u][4], x[u][6], r & 3),
+                          cmul(dif4(x[u][1], x[u][3], x[u][5], x[u][7], r & 3), w8r));
+        s[phys(t + u * step)] = to_sc(r ? cmul(y, __ldg(g.tw + (t + u * step) * r)) : y);
+      }
+    }
+    for (; t < g.m; t += step) {
+      cd x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = fetch(t + j * g.m);
+      const cd y = cadd(dif4(x[0], x[2], x[4], x[6], r & 3), cmul(dif4(x[1], x[3], x[5], x[7], r & 3), w8r));
+      s[phys(t)] = to_sc(r ? cmul(y, __ldg(g.tw + t * r)) : y);
+    }
+    return;
+  }
+  for (int t = threadIdx.x; t < g.m; t += step) {     // general R: sum_j x[t + j m] w_R^{jr}, times w_n^{tr}
     cd acc = mk(0.0, 0.0);
     for (int j = 0; j < g.R; ++j) {
       cd x = fetch(t + j * g.m);
       const int wi = ((j * r) & (g.R - 1)) * g.m;                      // w_R^{jr} = w_n^{(jr mod R) m}
       acc = cadd(acc, wi ? cmul(x, __ldg(g.tw + wi)) : x);
     }
-    s[phys(t)] = narrow(r ? cmul(acc, __ldg(g.tw + (int64_t)t * r)) : acc);   // w_n^{tr}, t r < n
+    s[phys(t)] = to_sc(r ? cmul(acc, __ldg(g.tw + (int64_t)t * r)) : acc);   // w_n^{tr}, t r < n
   }
 }
 
 // Transform the column in shared memory and feed every (slot, frequency, value) to the sink.
 // slot = padded in-place position, owned by the same thread on every call with the same geometry.
 template <class Sink>
-__device__ void transform_and_emit(float2* __restrict__ s, const FftGeom& g, int r, Sink& sink) {
+__device__ void transform_and_emit(sc* __restrict__ s, const FftGeom& g, int r, Sink& sink) {
   fft_smem_passes(s, g);
   const int n_blocks = g.m >> 4, fstep = g.m >> 4;
   for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) {
     cd x[kBlk];
 #pragma unroll
-    for (int e = 0; e < kBlk; ++e) x[e] = widen(s[b * (kBlk + 1) + e]);
+    for (int e = 0; e < kBlk; ++e) x[e] = to_cd(s[b * (kBlk + 1) + e]);
     fft16_registers(x);
     const int f0 = block_base_frequency(b, g);
 #pragma unroll
@@ -431,8 +508,8 @@ __device__ void flush_accumulator(const float* __restrict__ s_acc, float* __rest
 
 // Power-of-two n_t: P -> result in one kernel.
 template <int kMode>
-__global__ void __launch_bounds__(kFftThreads) fft_sed_kernel(SedArgs a, FftGeom g) {
-  extern __shared__ float2 s_data[];
+__global__ void __launch_bounds__(kFftThreads, kFftMinCtas) fft_sed_kernel(SedArgs a, FftGeom g) {
+  extern __shared__ sc s_data[];
   const ScaleOnly post{1.0 / (double)a.n_t};
   const int r = blockIdx.x % g.R;
   if (kMode == PSA_MODE_COHERENT) {          // block -> (k, pol, r)
@@ -465,11 +542,11 @@ __global__ void __launch_bounds__(kFftThreads) fft_sed_kernel(SedArgs a, FftGeom
 
 // Bluestein leg 1: column -> chirp, zero-pad, forward transform, times the chirp spectrum -> scratch.
 // block -> (column, r), column = (group, k, pol) flattened.
-__global__ void __launch_bounds__(kFftThreads) bluestein_forward_kernel(SedArgs a, FftGeom g, int n_k,
+__global__ void __launch_bounds__(kFftThreads, kFftMinCtas) bluestein_forward_kernel(SedArgs a, FftGeom g, int n_k,
                                                                         const double2* __restrict__ chirp,
                                                                         const double2* __restrict__ bhat,
                                                                         float2* __restrict__ scratch) {
-  extern __shared__ float2 s_data[];
+  extern __shared__ sc s_data[];
   const int r = blockIdx.x % g.R;
   const int col = blockIdx.x / g.R;
   const int pol = col % 3, k = (col / 3) % n_k, grp = col / (3 * n_k);
@@ -485,10 +562,10 @@ __global__ void __launch_bounds__(kFftThreads) bluestein_forward_kernel(SedArgs 
 
 // Bluestein leg 2: scratch -> inverse transform (by conjugation), unchirp, / n_t, SED assembly.
 template <int kMode>
-__global__ void __launch_bounds__(kFftThreads) bluestein_inverse_kernel(SedArgs a, FftGeom g, int n_k,
+__global__ void __launch_bounds__(kFftThreads, kFftMinCtas) bluestein_inverse_kernel(SedArgs a, FftGeom g, int n_k,
                                                                         const double2* __restrict__ chirp,
                                                                         const float2* __restrict__ scratch) {
-  extern __shared__ float2 s_data[];
+  extern __shared__ sc s_data[];
   const Unchirp post{chirp, a.n_t, 1.0 / (double)g.n_fft, (double)a.n_t};
   const int r = blockIdx.x % g.R;
   if (kMode == PSA_MODE_COHERENT) {
@@ -519,9 +596,9 @@ __global__ void __launch_bounds__(kFftThreads) bluestein_inverse_kernel(SedArgs 
 }
 
 // float64-in, float64-out forward transform of one column, natural order (the chirp spectrum of a plan)
-__global__ void __launch_bounds__(kFftThreads) fft_c2c_kernel(const double2* __restrict__ src, double2* __restrict__ dst,
+__global__ void __launch_bounds__(kFftThreads, kFftMinCtas) fft_c2c_kernel(const double2* __restrict__ src, double2* __restrict__ dst,
                                                               FftGeom g) {
-  extern __shared__ float2 s_data[];
+  extern __shared__ sc s_data[];
   const int r = blockIdx.x % g.R;
   FetchComplexD fetch{src};
   load_column(s_data, fetch, g, r);
@@ -580,8 +657,8 @@ static int64_t bluestein_length(int64_t n) {
 static int64_t sub_length(int64_t n_fft, int* R_out) {
   static const int64_t max_points = []() -> int64_t {     // tuning knob, see profiles/
     const char* env = getenv("PSA_FFT_MAX_POINTS");
-    int64_t v = env ? atoll(env) : kMaxSmemPoints;
-    if (v < 64 || v > kMaxSmemPoints || (v & (v - 1))) v = kMaxSmemPoints;
+    int64_t v = env ? atoll(env) : kDefaultSmemPoints;
+    if (v < 64 || v > kMaxSmemPoints || (v & (v - 1))) v = kDefaultSmemPoints;
     return v;
   }();
   int64_t m = n_fft;
@@ -612,7 +689,7 @@ static FftGeom make_geom(int64_t n_fft, const double2* tw) {   // tw = start of 
 
 static size_t smem_bytes(const FftGeom& g, bool with_acc) {
   const size_t padded = (size_t)(g.m + (g.m >> 4));
-  return padded * sizeof(float2) + (with_acc ? padded * sizeof(float) : 0);
+  return padded * sizeof(sc) + (with_acc ? padded * sizeof(float) : 0);
 }
 
 template <class K>

@@ -1,6 +1,10 @@
 // Trajectory ingest: float32 mean positions (bit-exact with NumPy) and the one-time split of the
 // projected time series into int8 digit planes laid out for TMA / tcgen05.  Both are HBM-bound.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace psa {
 
@@ -77,9 +81,136 @@ __global__ void __launch_bounds__(kMeanThreads) mean_positions_kernel(const floa
   }
 }
 
+// TMA variant (the product path whenever the row pitch is a multiple of 16 bytes, i.e. n_atoms % 4 == 0).
+// The register-staged kernel above spends 20 instructions per loaded word on addresses, predicates and
+// the shared-memory hand-over (ncu: issue slots 60 % busy, DRAM 47 %).  Here the copy engine does all
+// of that: one elected thread streams [kTmaRows x kTmaCols] boxes of the frame-major array into a ring
+// of shared-memory stages (cp.async.bulk.tensor.2d + mbarrier transaction counts), and the only other
+// threads of the CTA are the consumers - one per column - which perform the ordered float32 additions.
+// A CTA keeps kTmaStages * 16 KiB in flight, three CTAs per SM (scripts/mean_tune.py: 64 x 64 x 4 stages).
+#ifndef PSA_MEAN_TMA_COLS
+#define PSA_MEAN_TMA_COLS 64
+#endif
+#ifndef PSA_MEAN_TMA_ROWS
+#define PSA_MEAN_TMA_ROWS 64
+#endif
+#ifndef PSA_MEAN_TMA_STAGES
+#define PSA_MEAN_TMA_STAGES 4
+#endif
+constexpr int kTmaCols = PSA_MEAN_TMA_COLS;      // columns per CTA (multiple of 32, <= 256)
+constexpr int kTmaRows = PSA_MEAN_TMA_ROWS;      // frames per stage (<= 256)
+constexpr int kTmaStages = PSA_MEAN_TMA_STAGES;
+constexpr int kTmaConsumerWarps = kTmaCols / 32;
+constexpr int kTmaThreads = (kTmaConsumerWarps + 1) * 32;
+constexpr uint32_t kTmaStageBytes = kTmaCols * kTmaRows * sizeof(float);
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kTmaThreads) mean_positions_tma_kernel(const __grid_constant__ CUtensorMap map, int n_t,
+                                                                         int64_t n_cols, float* __restrict__ mean) {
+  extern __shared__ __align__(128) float tma_tiles[];        // [stage][row][col]
+  __shared__ uint64_t full_bar[kTmaStages], empty_bar[kTmaStages];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col0 = blockIdx.x * kTmaCols;
+  const int n_tiles = (n_t + kTmaRows - 1) / kTmaRows;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTmaStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kTmaConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kTmaConsumerWarps) {                            // producer: one thread feeds the ring
+    if (lane == 0) {
+      for (int i = 0; i < n_tiles; ++i) {
+        const int s = i % kTmaStages;
+        mbar_wait(&empty_bar[s], ((i / kTmaStages) & 1) ^ 1);
+        mbar_expect_tx(&full_bar[s], kTmaStageBytes);         // rows past n_t are zero-filled and still counted
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                smem_addr(tma_tiles + (size_t)s * kTmaRows * kTmaCols)),
+            "l"(&map), "r"(smem_addr(&full_bar[s])), "r"(col0), "r"(i * kTmaRows)
+            : "memory");
+      }
+    }
+    return;
+  }
+
+  const int c = warp * 32 + lane;
+  float acc = 0.0f;
+  for (int i = 0; i < n_tiles; ++i) {
+    const int s = i % kTmaStages;
+    mbar_wait(&full_bar[s], (i / kTmaStages) & 1);
+    const float* tp = tma_tiles + (size_t)s * kTmaRows * kTmaCols + c;
+    const int rows = min(kTmaRows, n_t - i * kTmaRows);
+    if (rows == kTmaRows) {
+#pragma unroll 16
+      for (int r = 0; r < kTmaRows; ++r) acc = __fadd_rn(acc, tp[r * kTmaCols]);
+    } else {
+      for (int r = 0; r < rows; ++r) acc = __fadd_rn(acc, tp[r * kTmaCols]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);                // this warp is done reading the stage
+  }
+  if (col0 + c < n_cols) mean[col0 + c] = __fdiv_rn(acc, (float)n_t);
+}
+
+static bool mean_use_tma(const float* pos, int64_t n_t, int64_t n_cols) {
+  static const bool disabled = []() {
+    const char* e = getenv("PSA_MEAN_IMPL");
+    return e != nullptr && strcmp(e, "simt") == 0;
+  }();
+  return !disabled && n_cols % 4 == 0 && (reinterpret_cast<uintptr_t>(pos) & 15) == 0 && n_t < (1 << 30) &&
+         n_cols < ((int64_t)1 << 31) && tensor_map_encoder() != nullptr;
+}
+
 int launch_mean_positions(const float* pos, int64_t n_t, int64_t n_a, float* mean, cudaStream_t s) {
   int64_t n_cols = n_a * 3;
   if (n_cols == 0) return PSA_OK;
+  if (mean_use_tma(pos, n_t, n_cols)) {
+    CUtensorMap map;
+    cuuint64_t dims[2] = {(cuuint64_t)n_cols, (cuuint64_t)n_t};
+    cuuint64_t strides[1] = {(cuuint64_t)n_cols * sizeof(float)};
+    cuuint32_t box[2] = {kTmaCols, kTmaRows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = tensor_map_encoder()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(pos), dims, strides, box,
+                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled failed with CUresult %d (mean positions, n_t=%lld n_cols=%lld)", (int)r,
+                (long long)n_t, (long long)n_cols);
+      return PSA_ERR_CUDA;
+    }
+    constexpr int smem = kTmaStages * (int)kTmaStageBytes;
+    PSA_CUDA(cudaFuncSetAttribute(mean_positions_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int64_t blocks = (n_cols + kTmaCols - 1) / kTmaCols;
+    mean_positions_tma_kernel<<<(unsigned)blocks, kTmaThreads, smem, s>>>(map, (int)n_t, n_cols, mean);
+    return launch_status("mean_positions_tma_kernel");
+  }
   int64_t blocks = (n_cols + kMeanCols - 1) / kMeanCols;
   constexpr int smem = 2 * kMeanRows * kMeanCols * (int)sizeof(float);   // 64 KiB: three CTAs per SM
   PSA_CUDA(cudaFuncSetAttribute(mean_positions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -181,20 +312,28 @@ __global__ void __launch_bounds__(256) digitize_kernel(const float* __restrict__
   for (int p = 0; p < 3; ++p) scale[p] = exp2f((float)(kFracBits - s_exp[p]));   // exact power of two
 
   const int64_t plane = n_t * pitch;                 // bytes of one (pol, slice) plane
+  // Digits without a carry chain: with Y = X + 0x00808080 the low three bytes of Y are d_i + 128 and the
+  // top byte is d3, so the bytes of Z = Y ^ 0x00808080 ARE the balanced digits (identical to
+  // balanced_digits(); |X| <= 2^30 leaves room for the bias).  Four atoms are then turned into four plane
+  // words by a 4 x 4 byte transpose (eight PRMTs).
   for (int64_t j0 = (int64_t)threadIdx.x * 4; j0 < pitch; j0 += (int64_t)blockDim.x * 4) {
     uint32_t word[3][kSlices] = {};
     if (j0 < n_sel) {
       float v[12];
       load_quad(row, mean, idx, j0, n_sel, v);      // entries past n_sel come back as zeros -> zero digits
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int p = 0; p < 3; ++p) {
+        uint32_t z[4];
 #pragma unroll
-        for (int p = 0; p < 3; ++p) {
-          int8_t d[kSlices];
-          balanced_digits(__float2int_rn(v[q * 3 + p] * scale[p]), d);
-#pragma unroll
-          for (int sl = 0; sl < kSlices; ++sl) word[p][sl] |= (uint32_t)(uint8_t)d[sl] << (8 * q);
-        }
+        for (int q = 0; q < 4; ++q)
+          z[q] = ((uint32_t)__float2int_rn(v[q * 3 + p] * scale[p]) + 0x00808080u) ^ 0x00808080u;
+        const uint32_t lo01 = __byte_perm(z[0], z[1], 0x5140), hi01 = __byte_perm(z[0], z[1], 0x7362);
+        const uint32_t lo23 = __byte_perm(z[2], z[3], 0x5140), hi23 = __byte_perm(z[2], z[3], 0x7362);
+        word[p][0] = __byte_perm(lo01, lo23, 0x5410);
+        word[p][1] = __byte_perm(lo01, lo23, 0x7632);
+        word[p][2] = __byte_perm(hi01, hi23, 0x5410);
+        word[p][3] = __byte_perm(hi01, hi23, 0x7632);
+      }
     }
 #pragma unroll
     for (int p = 0; p < 3; ++p)

@@ -18,6 +18,7 @@
 #include <cuda.h>
 
 #include "project_common.cuh"
+#include "tma.cuh"
 
 namespace psa {
 namespace tc2 {
@@ -309,21 +310,7 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tmap_phase, const __grid_
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = []() -> EncodeTiledFn {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    return reinterpret_cast<EncodeTiledFn>(p);
-  }();
-  return fn;
-}
+static EncodeTiledFn encode_fn() { return tensor_map_encoder(); }
 
 // 3-D map over int8 digit planes [outer][mid][n_sel], row pitch `pitch` bytes, box 64 x box_rows x 4.
 static int make_map(CUtensorMap* map, const int8_t* base, int64_t n_sel, int64_t pitch, int64_t mid, int64_t mid_alloc,

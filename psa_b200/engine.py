@@ -45,12 +45,20 @@ class Engine:
         self.project_impl = project_impl
         self._plans: Dict[int, torch.Tensor] = {}
         self._fft_ws: Optional[torch.Tensor] = None
+        self._copy_stream: Optional[torch.cuda.Stream] = None
         self.launches = 0          # kernels launched through this engine (bench reports it)
         self.profile: Optional[Dict[str, List[Tuple[torch.cuda.Event, torch.cuda.Event, int]]]] = None
 
     # -- helpers
     def stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    @property
+    def copy_stream(self) -> "torch.cuda.Stream":
+        """Side stream for result copies that overlap with compute (created on first use)."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        return self._copy_stream
 
     def empty(self, shape, dtype) -> torch.Tensor:
         return torch.empty(shape, dtype=dtype, device=self.device)
@@ -283,19 +291,28 @@ class DeviceTrajectory:
 
 
 def sed_on_device(traj: DeviceTrajectory, k_vecs: np.ndarray, groups: Sequence[Optional[np.ndarray]],
-                  complex_out: bool, use_displacements: bool, k_chunk: int = K_CHUNK_CAP) -> torch.Tensor:
+                  complex_out: bool, use_displacements: bool, k_chunk: int = K_CHUNK_CAP,
+                  host_out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
     """Run the projection + FFT pipeline; returns the device-resident result.
 
     ``groups``: atom index arrays (``None`` = all atoms).  ``complex_out`` -> complex64
     ``(n_t, n_k, 3)`` from the single group; otherwise float32 ``(n_t, n_k)`` summed over groups.
+
+    With ``host_out`` (a pinned host tensor of the result's shape) nothing result-sized is kept on the
+    device: every k-chunk is transformed into one of two chunk buffers and copied into its column slice
+    of ``host_out`` on a side stream while the next chunk is projected (the reference fills
+    ``full_sed_data[:, k0:k1]`` chunk by chunk as well, sed_calculator.py:287-327).  Returns ``None``;
+    the caller synchronises ``traj.engine.copy_stream`` before reading ``host_out``.
     """
     eng = traj.engine
     n_t, n_k = traj.n_t, int(k_vecs.shape[0])
+    shape = (n_t, n_k, 3) if complex_out else (n_t, n_k)
+    dtype = torch.complex64 if complex_out else torch.float32
     if complex_out:
         assert len(groups) == 1
-        out = torch.empty((n_t, n_k, 3), dtype=torch.complex64, device=eng.device)
-    else:
-        out = torch.empty((n_t, n_k), dtype=torch.float32, device=eng.device)
+    if host_out is not None:
+        assert tuple(host_out.shape) == shape and host_out.dtype == dtype and host_out.is_pinned()
+    out = None if host_out is not None else torch.empty(shape, dtype=dtype, device=eng.device)
     if n_k == 0:
         return out
     mean, entries = traj.prepare(groups, use_displacements)
@@ -307,7 +324,12 @@ def sed_on_device(traj: DeviceTrajectory, k_vecs: np.ndarray, groups: Sequence[O
     group_stride = rows_alloc * 3 * ldp
     adig_bufs: Dict[int, torch.Tensor] = {}
     mode = _lib.MODE_COHERENT if complex_out else _lib.MODE_INCOHERENT
-    for k0 in range(0, n_k, kc):
+    if host_out is not None:
+        elem = (3 if complex_out else 1) * host_out.element_size()       # bytes per (f, k)
+        chunk_bufs = [torch.empty((n_t, kc) + shape[2:], dtype=dtype, device=eng.device) for _ in range(2)]
+        drained = [None, None]                                           # copy-stream events per buffer
+        compute, copy = torch.cuda.current_stream(eng.device), eng.copy_stream
+    for ci, k0 in enumerate(range(0, n_k, kc)):
         nk = min(kc, n_k - k0)
         for g, (idx_dev, n_sel, pitch, dig, expo) in enumerate(entries):
             adig = adig_bufs.get(pitch)
@@ -315,5 +337,21 @@ def sed_on_device(traj: DeviceTrajectory, k_vecs: np.ndarray, groups: Sequence[O
                 adig = adig_bufs[pitch] = eng.empty((4, rows_alloc, pitch), torch.int8)
             eng.phase_digits(kv_dev[k0:k0 + nk], mean, idx_dev, n_sel, pitch, rows_alloc, out=adig)
             eng.project(adig, 2 * nk, rows_alloc, dig, expo, n_t, n_sel, pitch, P[g], ldp)
-        eng.fft_sed(P, len(entries), group_stride, nk, n_t, ldp, mode, out, n_k, k0)
+        if host_out is None:
+            eng.fft_sed(P, len(entries), group_stride, nk, n_t, ldp, mode, out, n_k, k0)
+            continue
+        buf = chunk_bufs[ci & 1]
+        if drained[ci & 1] is not None:
+            compute.wait_event(drained[ci & 1])                          # its previous contents are on the host
+        eng.fft_sed(P, len(entries), group_stride, nk, n_t, ldp, mode, buf, kc, 0)
+        ready = torch.cuda.Event()
+        ready.record(compute)
+        copy.wait_event(ready)
+        _lib.call("psa_copy_rows", host_out.data_ptr() + k0 * elem, n_k * elem, buf.data_ptr(), kc * elem,
+                  nk * elem, n_t, copy.cuda_stream)
+        drained[ci & 1] = torch.cuda.Event()
+        drained[ci & 1].record(copy)
+    if host_out is not None:
+        for b in chunk_bufs:                     # the copy stream still reads them: keep the allocator from reusing
+            b.record_stream(copy)
     return out

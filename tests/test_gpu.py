@@ -326,6 +326,22 @@ def test_chunk_invariance_is_bitwise(gold_si):
     np.testing.assert_array_equal(a, b)
 
 
+def test_streamed_chunks_match_single_chunk(gold_si):
+    """A k-set longer than one chunk is streamed chunk by chunk into the pinned host result on a side
+    stream; ragged last chunk, both result kinds, and the device-resident path give the same bits."""
+    calc = _calc(gold_si)
+    kv = gold_si["kpath_110_vecs"]
+    assert len(kv) % 7 != 0
+    for kwargs in (dict(), dict(basis_atom_types=[1, 2], summation_mode="incoherent")):
+        whole = calc.calculate(np.zeros(len(kv)), kv, k_chunk_size=500, **kwargs)
+        streamed = calc.calculate(np.zeros(len(kv)), kv, k_chunk_size=7, **kwargs)
+        assert streamed.sed.shape == whole.sed.shape and streamed.is_complex == whole.is_complex
+        np.testing.assert_array_equal(streamed.sed, whole.sed)
+        dev, _, _ = calc._calculate_device(kv, None, kwargs.get("basis_atom_types"),
+                                           kwargs.get("summation_mode", "coherent"), 7)
+        np.testing.assert_array_equal(dev.cpu().numpy(), whole.sed)
+
+
 def test_chiral_sed_facade(gold_gr):
     calc = _calc(gold_gr)
     res = calc.calculate_chiral_sed([1, 0, 0], bz_coverage=4.0, n_k=10, chiral_axis="z")
