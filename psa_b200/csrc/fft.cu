@@ -12,7 +12,19 @@
 // and ONE rounding to float32 when the spectrum is stored (scripts/fft_accuracy.py: the rms error
 // equals NumPy's at every length).  B200 runs FP64 at half the FP32 rate, so this costs little; the
 // float32 <-> float64 conversions (16-lane XU pipe) are confined to the load and the final store.
-// -DPSA_FFT_STORE64=0 rebuilds the earlier float32-storage variant (rounds once per pass) for A/B runs.
+//
+// Where the time goes (ncu, 3000 columns of 16384 points, 0.76 ms): ~190 thread instructions per
+// point, issue slots 34 % busy, FP64 pipe 20 %, XU 16 %, L1 data pipe 59 %; half of the stall
+// samples sit in the load-time split (waiting on L2), a fifth in the scattered result store.  The
+// kernel is latency-bound at 24 warps per SM (80 registers per thread for float64 butterflies).
+// Tried and measured slower or equal in round 1 (scripts/fft_tune.py), and therefore not kept:
+//   * float32 storage with float64 butterflies (same speed, 2x the rounding error);
+//   * clusters of 2-8 ADJACENT columns exchanging spectra through distributed shared memory so that
+//     the frequency-major result is written in 32-64 byte runs (0.80-0.86 ms vs 0.76 ms);
+//   * the R CTAs of ONE column as a cluster, each loading 1/R of the samples and gathering the rest
+//     from its peers' shared memory instead of re-reading them from L2 (0.90 ms vs 0.78 ms);
+//   * twiddles factored into two 64-entry shared-memory tables instead of L2-resident per-pass tables
+//     (0.775 ms vs 0.765 ms).
 //
 // Power-of-two core (forward, decimation in frequency, in place, m = 2^s points, 16 <= m <= 16384):
 //   * shared-memory passes of radix 8 (one leading radix-2 or radix-4 pass when (s-4) % 3 != 0) down
@@ -41,28 +53,20 @@
 
 namespace psa {
 
-#ifndef PSA_FFT_STORE64
-#define PSA_FFT_STORE64 1
-#endif
 #ifndef PSA_FFT_THREADS
-#define PSA_FFT_THREADS (PSA_FFT_STORE64 ? 256 : 512)
+#define PSA_FFT_THREADS 256
 #endif
 #ifndef PSA_FFT_UNROLL
 #define PSA_FFT_UNROLL 2
 #endif
 #ifndef PSA_FFT_MIN_CTAS
-#define PSA_FFT_MIN_CTAS (PSA_FFT_STORE64 ? 3 : 1)
+#define PSA_FFT_MIN_CTAS 3
 #endif
 constexpr int kFftThreads = PSA_FFT_THREADS;
 constexpr int kFftUnroll = PSA_FFT_UNROLL;
 constexpr int kFftMinCtas = PSA_FFT_MIN_CTAS;
-#if PSA_FFT_STORE64
 constexpr int64_t kMaxSmemPoints = 8192;       // complex128 points that fit one CTA (128 KiB + padding)
 constexpr int64_t kDefaultSmemPoints = 4096;   // 68 KiB: three CTAs per SM
-#else
-constexpr int64_t kMaxSmemPoints = 16384;      // complex64 points that fit one CTA (128 KiB + padding)
-constexpr int64_t kDefaultSmemPoints = 16384;
-#endif
 constexpr int64_t kMaxTransform = (int64_t)1 << 20;
 constexpr int kBlk = 16;                    // points finished in registers per thread
 constexpr int kMaxPasses = 5;
@@ -76,15 +80,9 @@ struct cd {
 __device__ __forceinline__ cd mk(double x, double y) { cd r; r.x = x; r.y = y; return r; }
 __device__ __forceinline__ cd widen(float2 a) { return mk((double)a.x, (double)a.y); }
 __device__ __forceinline__ float2 narrow(cd a) { return make_float2((float)a.x, (float)a.y); }
-#if PSA_FFT_STORE64
 using sc = double2;
 __device__ __forceinline__ cd to_cd(sc a) { return mk(a.x, a.y); }
 __device__ __forceinline__ sc to_sc(cd a) { return make_double2(a.x, a.y); }
-#else
-using sc = float2;
-__device__ __forceinline__ cd to_cd(sc a) { return widen(a); }
-__device__ __forceinline__ sc to_sc(cd a) { return narrow(a); }
-#endif
 __device__ __forceinline__ cd cmul(cd a, cd b) { return mk(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x)); }
 __device__ __forceinline__ cd cmul(cd a, double2 b) { return mk(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x)); }
 __device__ __forceinline__ cd cmul_conj(cd a, cd b) { return mk(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -a.x * b.y)); }   // a conj(b)
@@ -484,6 +482,7 @@ struct SedArgs {
   int n_t;
   void* out;
   int64_t n_k_total, k_offset;
+  double inv_n_t;           // 1 / n_t from the host: a float64 division per CTA showed up as 5 % of the stall samples
 };
 
 __device__ __forceinline__ void column_rows(const SedArgs& a, int g, int k, int pol, const float*& re, const float*& im) {
@@ -510,7 +509,7 @@ __device__ void flush_accumulator(const float* __restrict__ s_acc, float* __rest
 template <int kMode>
 __global__ void __launch_bounds__(kFftThreads, kFftMinCtas) fft_sed_kernel(SedArgs a, FftGeom g) {
   extern __shared__ sc s_data[];
-  const ScaleOnly post{1.0 / (double)a.n_t};
+  const ScaleOnly post{a.inv_n_t};
   const int r = blockIdx.x % g.R;
   if (kMode == PSA_MODE_COHERENT) {          // block -> (k, pol, r)
     const int pol = (blockIdx.x / g.R) % 3, k = blockIdx.x / (3 * g.R);
@@ -763,7 +762,7 @@ int launch_fft(const float* P, int64_t n_groups, int64_t group_stride, int64_t n
               "psa_fft_sed: workspace of %lld bytes required for n_t=%lld (got %lld)", (long long)need,
               (long long)n_t, (long long)workspace_bytes);
   const double2* plan = reinterpret_cast<const double2*>(plan_buf);
-  SedArgs a{P, (int)n_groups, group_stride, ldp, (int)n_t, out, n_k_total, k_offset};
+  SedArgs a{P, (int)n_groups, group_stride, ldp, (int)n_t, out, n_k_total, k_offset, 1.0 / (double)n_t};
   const bool coherent = mode == PSA_MODE_COHERENT;
 
   if (need == 0) {                                       // power of two: one fused kernel

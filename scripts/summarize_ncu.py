@@ -69,7 +69,7 @@ def full(src, dst, workload=None):
     Path(dst).write_text("\n".join(out) + "\n")
     print("\n".join(out))
     if workload:
-        api = {"mean_positions_kernel": "psa_mean_positions", "digitize_kernel": "psa_digitize",
+        api = {"mean_positions_kernel": "psa_mean_positions", "mean_positions_tma_kernel": "psa_mean_positions", "digitize_kernel": "psa_digitize",
                "phase_digits_kernel": "psa_phase_digits", "tc::project_tc_kernel": "psa_project",
                "fft_sed_kernel<0>": "psa_fft_sed", "fft_sed_kernel<1>": "psa_fft_sed"}
         p = Path(dst).parent / "ncu_traffic.json"
