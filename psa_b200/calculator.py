@@ -224,11 +224,13 @@ class SEDCalculator:
     def reconstruct(self, k_dir_spec, targets: Sequence[Tuple[float, float]], char_len_k_path: Optional[float],
                     nk_on_path: int = 100, bz_cov_ised: float = 1.0, basis_atom_idx_ised=None,
                     basis_atom_types_ised=None, rescale_factor: Union[str, float] = 1.0,
-                    n_recon_frames: int = 100) -> List[Dict]:
+                    n_recon_frames: int = 100, keep_on_device: bool = False) -> List[Dict]:
         """Batched inverse projection: one entry per ``(k_target, w_target)`` with the reconstructed
         frames ``(n_recon_frames, n_atoms, 3)`` float32 plus the matched indices.  The projection of all
         distinct matched k-points is done in one pass per atom group instead of one full SED per group
-        per call (reference: sed_calculator.py:451-499)."""
+        per call (reference: sed_calculator.py:451-499).  ``keep_on_device`` leaves ``frames`` as CUDA
+        tensors (for device-side consumers; the host copy of many large frame sets is bound by the
+        first-touch cost of fresh host memory, not by the GPU)."""
         traj = self.traj
         n_atoms = traj.n_atoms
         k_hat = parse_direction(k_dir_spec)
@@ -271,31 +273,44 @@ class SEDCalculator:
                     den += int(g.size)
                 std_scale = num / den if den > 0 else 0.0
 
-            for ti, (kt, wt) in enumerate(targets):
-                amp_atom = np.zeros((n_atoms, 3), np.complex128)
-                for g, a in zip(recon_groups, amps):
-                    amp_atom[np.unique(g)] += a[ti].astype(np.complex128)[None, :]
-                amp_dev = torch.from_numpy(np.ascontiguousarray(amp_atom.view(np.float64).reshape(n_atoms, 3, 2))
-                                           ).to(eng.device)
-                k_act = float(k_mags[k_idx[ti]])
-                frames = eng.empty((n_recon_frames, n_atoms, 3), torch.float32)
-                scale = 1.0
-                if auto:
-                    self._ised_kernel(mean, amp_dev, khat_dev, k_act, 1.0, 0, n_atoms, n_recon_frames, frames)
-                    mx = eng.empty((1,), torch.float32)
-                    _lib.call("psa_absmax", frames.data_ptr(), frames.numel(), mx.data_ptr(), eng.stream())
-                    max_amp = float(mx.item())
-                    if max_amp > 1e-9:
-                        scale = 1.0 / max_amp
-                        if std_scale > 1e-9:
-                            scale *= std_scale
-                    else:
-                        logger.warning("iSED: Max wiggle amp near zero. Auto-rescaling ineffective.")
-                elif isinstance(rescale_factor, (int, float)):
-                    scale = float(rescale_factor)
-                self._ised_kernel(mean, amp_dev, khat_dev, k_act, scale, 1, n_atoms, n_recon_frames, frames)
-                results.append(dict(frames=self._to_host(frames), k_index=k_idx[ti], w_index=w_idx[ti],
-                                    k_actual=k_act, w_actual=float(freqs[w_idx[ti]]), k_target=kt, w_target=wt))
+            # per-atom amplitudes of every target at once: (n_targets, n_atoms, 3) complex128, uploaded in batches
+            members = [np.unique(g) for g in recon_groups]                     # the reference adds a group once per atom
+            batch = max(1, (256 << 20) // (n_atoms * 48))
+            for t0 in range(0, len(targets), batch):
+                t1 = min(len(targets), t0 + batch)
+                amp_all = np.zeros((t1 - t0, n_atoms, 3), np.complex128)
+                for m, a in zip(members, amps):
+                    amp_all[:, m, :] += a[t0:t1].astype(np.complex128)[:, None, :]
+                amp_dev_all = torch.from_numpy(amp_all.view(np.float64).reshape(t1 - t0, n_atoms, 3, 2)).to(eng.device)
+                for ti in range(t0, t1):
+                    kt, wt = targets[ti]
+                    amp_dev = amp_dev_all[ti - t0]
+                    k_act = float(k_mags[k_idx[ti]])
+                    frames = eng.empty((n_recon_frames, n_atoms, 3), torch.float32)
+                    scale = 1.0
+                    if auto:
+                        self._ised_kernel(mean, amp_dev, khat_dev, k_act, 1.0, 0, n_atoms, n_recon_frames, frames)
+                        mx = eng.empty((1,), torch.float32)
+                        _lib.call("psa_absmax", frames.data_ptr(), frames.numel(), mx.data_ptr(), eng.stream())
+                        max_amp = float(mx.item())
+                        if max_amp > 1e-9:
+                            scale = 1.0 / max_amp
+                            if std_scale > 1e-9:
+                                scale *= std_scale
+                        else:
+                            logger.warning("iSED: Max wiggle amp near zero. Auto-rescaling ineffective.")
+                    elif isinstance(rescale_factor, (int, float)):
+                        scale = float(rescale_factor)
+                    self._ised_kernel(mean, amp_dev, khat_dev, k_act, scale, 1, n_atoms, n_recon_frames, frames)
+                    if keep_on_device:
+                        host = frames
+                    elif len(targets) == 1:
+                        host = self._to_host(frames)
+                    else:                       # many frame sets: plain host arrays (a pinned buffer per set costs more than the copy)
+                        host = np.empty(tuple(frames.shape), np.float32)
+                        torch.from_numpy(host).copy_(frames)
+                    results.append(dict(frames=host, k_index=k_idx[ti], w_index=w_idx[ti], k_actual=k_act,
+                                        w_actual=float(freqs[w_idx[ti]]), k_target=kt, w_target=wt))
         return results
 
     def _ised_kernel(self, mean, amp_dev, khat_dev, k_act, scale, add_mean, n_atoms, n_frames, out) -> None:

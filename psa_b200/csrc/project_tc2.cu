@@ -273,30 +273,44 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tmap_phase, const __grid_
       const bool t_ok = t < n_t;
       const int e = t_ok ? __ldg(expo + (int64_t)tc.pol * n_t + t) : kExpMin;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      const int c_end = min(tc.n_cols, part * EPI_COLS + EPI_COLS);
-#pragma unroll 1
-      for (int c0 = part * EPI_COLS; c0 < c_end; c0 += 16) {
-        uint32_t r0[16], r1[16], r2[16], r3[16];
-        PSA_TMEM_LD16(r0, lane_addr + 0 * BN + c0);
-        PSA_TMEM_LD16(r1, lane_addr + 1 * BN + c0);
-        PSA_TMEM_LD16(r2, lane_addr + 2 * BN + c0);
-        PSA_TMEM_LD16(r3, lane_addr + 3 * BN + c0);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (t_ok) {
-          const int row0 = tc.row0 + c0;
-          float* dst = P + ((int64_t)row0 * 3 + tc.pol) * ldp + t;
+      const int c_begin = part * EPI_COLS, c_end = min(tc.n_cols, c_begin + EPI_COLS);
+      // Drain first, store later: the accumulators are read and recombined into EPI_COLS float32 values
+      // per thread, the TMEM is handed back to the MMA issuer, and only then do the (slow) global stores
+      // run - under the next tile's MMAs instead of in front of them.
+      float v[EPI_COLS];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (row0 + i < rows) {
-              float v = combine_classes((int32_t)r0[i], (int32_t)r1[i], (int32_t)r2[i], (int32_t)r3[i], e);
-              float* d = dst + (int64_t)i * 3 * ldp;
-              *d = accumulate ? __fadd_rn(*d, v) : v;
-            }
-          }
+      for (int ch = 0; ch < EPI_COLS / 16; ++ch) {
+        const int c0 = c_begin + ch * 16;
+        if (c0 < c_end) {                                      // warp-uniform
+          uint32_t r0[16], r1[16], r2[16], r3[16];
+          PSA_TMEM_LD16(r0, lane_addr + 0 * BN + c0);
+          PSA_TMEM_LD16(r1, lane_addr + 1 * BN + c0);
+          PSA_TMEM_LD16(r2, lane_addr + 2 * BN + c0);
+          PSA_TMEM_LD16(r3, lane_addr + 3 * BN + c0);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            v[ch * 16 + i] = combine_classes((int32_t)r0[i], (int32_t)r1[i], (int32_t)r2[i], (int32_t)r3[i], e);
         }
       }
       tc_fence_before();
       mbar_arrive_cluster(tmem_empty, 0);                      // leader's barrier, remote for rank 1
+      if (t_ok) {
+#pragma unroll
+        for (int ch = 0; ch < EPI_COLS / 16; ++ch) {
+          const int row0 = tc.row0 + c_begin + ch * 16;
+          if (c_begin + ch * 16 < c_end) {
+            float* dst = P + ((int64_t)row0 * 3 + tc.pol) * ldp + t;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (row0 + i < rows) {
+                float* d = dst + (int64_t)i * 3 * ldp;
+                *d = accumulate ? __fadd_rn(*d, v[ch * 16 + i]) : v[ch * 16 + i];
+              }
+            }
+          }
+        }
+      }
       tile_phase ^= 1;
     }
   }
