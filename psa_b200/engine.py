@@ -292,7 +292,7 @@ class DeviceTrajectory:
 
 def sed_on_device(traj: DeviceTrajectory, k_vecs: np.ndarray, groups: Sequence[Optional[np.ndarray]],
                   complex_out: bool, use_displacements: bool, k_chunk: int = K_CHUNK_CAP,
-                  host_out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+                  host_out: Optional[torch.Tensor] = None, n_rows: Optional[int] = None) -> Optional[torch.Tensor]:
     """Run the projection + FFT pipeline; returns the device-resident result.
 
     ``groups``: atom index arrays (``None`` = all atoms).  ``complex_out`` -> complex64
@@ -302,7 +302,9 @@ def sed_on_device(traj: DeviceTrajectory, k_vecs: np.ndarray, groups: Sequence[O
     device: every k-chunk is transformed into one of two chunk buffers and copied into its column slice
     of ``host_out`` on a side stream while the next chunk is projected (the reference fills
     ``full_sed_data[:, k0:k1]`` chunk by chunk as well, sed_calculator.py:287-327).  Returns ``None``;
-    the caller synchronises ``traj.engine.copy_stream`` before reading ``host_out``.
+    the caller synchronises ``traj.engine.copy_stream`` before reading ``host_out``.  ``n_rows`` limits the
+    streamed copy to the first ``n_rows`` frequency rows (``host_out`` then has that many rows): fftfreq
+    order puts 0 <= f <= f_max first, so a frequency crop never leaves the device.
     """
     eng = traj.engine
     n_t, n_k = traj.n_t, int(k_vecs.shape[0])
@@ -310,8 +312,9 @@ def sed_on_device(traj: DeviceTrajectory, k_vecs: np.ndarray, groups: Sequence[O
     dtype = torch.complex64 if complex_out else torch.float32
     if complex_out:
         assert len(groups) == 1
+    n_rows = n_t if n_rows is None else max(0, min(int(n_rows), n_t))
     if host_out is not None:
-        assert tuple(host_out.shape) == shape and host_out.dtype == dtype and host_out.is_pinned()
+        assert tuple(host_out.shape) == (n_rows,) + shape[1:] and host_out.dtype == dtype and host_out.is_pinned()
     out = None if host_out is not None else torch.empty(shape, dtype=dtype, device=eng.device)
     if n_k == 0:
         return out
@@ -348,7 +351,7 @@ def sed_on_device(traj: DeviceTrajectory, k_vecs: np.ndarray, groups: Sequence[O
         ready.record(compute)
         copy.wait_event(ready)
         _lib.call("psa_copy_rows", host_out.data_ptr() + k0 * elem, n_k * elem, buf.data_ptr(), kc * elem,
-                  nk * elem, n_t, copy.cuda_stream)
+                  nk * elem, n_rows, copy.cuda_stream)
         drained[ci & 1] = torch.cuda.Event()
         drained[ci & 1].record(copy)
     if host_out is not None:

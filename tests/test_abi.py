@@ -46,6 +46,9 @@ def test_bad_arguments_are_reported_not_crashed(lib):
     assert status == _lib.ERR_BAD_ARG and b"psa_project" in lib.psa_last_error()
     with pytest.raises(ValueError):
         _lib.check(lib.psa_digitize(None, None, None, 1, 1, 1, 64, None, None, None))
+    # strided row copy: empty extents are a no-op, a row wider than its pitch is refused
+    assert lib.psa_copy_rows(None, 0, None, 0, 0, 0, None) == 0
+    assert lib.psa_copy_rows(1, 8, 1, 16, 12, 4, None) == _lib.ERR_BAD_ARG and b"psa_copy_rows" in lib.psa_last_error()
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

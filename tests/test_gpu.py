@@ -29,12 +29,24 @@ def dev(eng, arr):
 
 
 # ------------------------------------------------------------------ ingest
-@pytest.mark.parametrize("n_t,n_a", [(256, 64), (3001, 37), (17, 1000)])
+# (n_atoms % 4 == 0 -> TMA kernel, otherwise the register-staged one; ragged last tiles in both directions)
+@pytest.mark.parametrize("n_t,n_a", [(256, 64), (3001, 37), (17, 1000), (3001, 44), (1000, 4), (2, 8), (64 * 9, 20)])
 def test_mean_positions_bit_exact(eng, n_t, n_a):
     rng = np.random.default_rng(n_t)
     pos = (rng.random((n_t, n_a, 3)) * 43.4 + rng.standard_normal((n_t, n_a, 3)) * 0.01).astype(np.float32)
     got = eng.mean_positions(dev(eng, pos)).cpu().numpy()
     np.testing.assert_array_equal(got, np.mean(pos, axis=0, dtype=np.float32))
+
+
+def test_mean_positions_unaligned_base_uses_fallback(eng):
+    """A trajectory whose first element is not 16-byte aligned cannot be described by a tensor map."""
+    rng = np.random.default_rng(3)
+    n_t, n_a = 300, 16
+    flat = torch.from_numpy(rng.standard_normal(n_t * n_a * 3 + 1).astype(np.float32)).to(eng.device)
+    pos = flat[1:].view(n_t, n_a, 3)
+    assert pos.data_ptr() % 16 != 0
+    got = eng.mean_positions(pos).cpu().numpy()
+    np.testing.assert_array_equal(got, np.mean(pos.cpu().numpy(), axis=0, dtype=np.float32))
 
 
 @pytest.mark.parametrize("case", ["all", "subset", "displacement", "zeros"])
@@ -340,6 +352,27 @@ def test_streamed_chunks_match_single_chunk(gold_si):
         dev, _, _ = calc._calculate_device(kv, None, kwargs.get("basis_atom_types"),
                                            kwargs.get("summation_mode", "coherent"), 7)
         np.testing.assert_array_equal(dev.cpu().numpy(), whole.sed)
+
+
+def test_intensity_map_on_device(gold_si):
+    """N3: sum_pol |S|^2 straight from the FFT kernel's epilogue, cropped to 0 <= f <= max_freq, streamed or not."""
+    calc = _calc(gold_si)
+    kv = gold_si["kpath_110_vecs"]
+    full = calc.calculate(np.zeros(len(kv)), kv)
+    want = O.intensity(full.sed)
+    got = calc.calculate_intensity(np.zeros(len(kv)), kv)
+    assert got.sed.shape == want.shape and got.sed.dtype == np.float32 and not got.is_complex
+    np.testing.assert_allclose(got.sed, want, rtol=2e-6, atol=1e-9 * want.max())
+    np.testing.assert_array_equal(got.freqs, full.freqs)
+    f_max = float(full.freqs[full.freqs > 0][len(full.freqs) // 5])
+    keep = (full.freqs >= 0) & (full.freqs <= f_max)
+    for chunk in (500, 7):                                  # single chunk / streamed ragged chunks
+        crop = calc.calculate_intensity(np.zeros(len(kv)), kv, max_freq=f_max, k_chunk_size=chunk)
+        np.testing.assert_array_equal(crop.freqs, full.freqs[keep])
+        np.testing.assert_array_equal(crop.sed, got.sed[keep])
+    inc = calc.calculate(np.zeros(len(kv)), kv, basis_atom_types=[1, 2], summation_mode="incoherent")
+    inc_map = calc.calculate_intensity(np.zeros(len(kv)), kv, basis_atom_types=[1, 2], summation_mode="incoherent")
+    np.testing.assert_array_equal(inc_map.sed, inc.sed)
 
 
 def test_chiral_sed_facade(gold_gr):
