@@ -26,12 +26,14 @@
 //   * twiddles factored into two 64-entry shared-memory tables instead of L2-resident per-pass tables
 //     (0.775 ms vs 0.765 ms).
 //
-// Power-of-two core (forward, decimation in frequency, in place, m = 2^s points, 16 <= m <= 16384):
-//   * shared-memory passes of radix 8 (one leading radix-2 or radix-4 pass when (s-4) % 3 != 0) down
-//     to contiguous blocks of 16.  Butterfly legs are >= 16 elements apart, so every half-warp (the
-//     unit of a 64-bit shared access) touches 16 consecutive elements: conflict-free.
-//   * final stage: each thread pulls one contiguous 16-point block into registers, finishes it with
-//     radix 4 x 4 and hands the 16 results (digit-reversed frequency index) to a sink.  The array is
+// Mixed-radix core (forward, decimation in frequency, in place, m = blk * 2^a 3^b 5^c points with
+// blk = 16, 8 or 4, m <= 4096): covers the frame counts molecular-dynamics runs actually produce
+// (10 000, 20 000, 50 000 ...) as well as the powers of two.
+//   * shared-memory passes of radix 8 (one leading radix-2 or radix-4 pass), then 5, then 3, down to
+//     contiguous blocks of blk points.  Consecutive threads take consecutive butterflies, so every
+//     quarter-warp (the unit of a 128-bit shared access) touches consecutive elements: conflict-free.
+//   * final stage: each thread pulls one contiguous block into registers, finishes it (radix 4 x 4,
+//     8 or 4) and hands the results (digit-reversed frequency index) to a sink.  The array is
 //     padded by one element per 16 (index p lives at p + p/16), which makes these per-thread
 //     contiguous reads conflict-free as well.
 //   * a CTA transforms at most 4096 points (68 KiB of float64 storage, three CTAs per SM).  Longer
@@ -41,8 +43,8 @@
 //   * twiddles: float64 tables, per pass and contiguous in the butterfly index (a warp reads short
 //     contiguous runs), plus w_n^j for the load-time split.
 //
-// Frame counts that are not a power of two (the reference accepts any n_t through pocketfft) use
-// Bluestein's chirp-z identity on top of the same core: with b_t = exp(i pi t^2 / n),
+// Frame counts the core cannot factor (odd, or with a prime factor above 5; the reference accepts any
+// n_t through pocketfft) use Bluestein's chirp-z identity on top of it: with b_t = exp(i pi t^2 / n),
 //   X_f = conj(b_f) * sum_t (x_t conj(b_t)) b_{f-t},
 // i.e. one forward transform of length M >= 2n-1 (M = 2^s), a point-wise product with the
 // precomputed spectrum of b, and one inverse transform; the chirped spectrum of each column makes
@@ -69,7 +71,7 @@ constexpr int64_t kMaxSmemPoints = 8192;       // complex128 points that fit one
 constexpr int64_t kDefaultSmemPoints = 4096;   // 68 KiB: three CTAs per SM
 constexpr int64_t kMaxTransform = (int64_t)1 << 20;
 constexpr int kBlk = 16;                    // points finished in registers per thread
-constexpr int kMaxPasses = 5;
+constexpr int kMaxPasses = 6;
 
 // ---------------------------------------------------------------------------------------------
 // complex helpers (float64 arithmetic; sc = the shared-memory element)
@@ -114,57 +116,101 @@ __device__ __forceinline__ void bfly8(cd (&a)[8]) {
   a[1] = v0; a[3] = v1; a[5] = v2; a[7] = v3;
 }
 
+__device__ __forceinline__ void bfly3(cd& a0, cd& a1, cd& a2) {           // w3 = -1/2 - i sin(2 pi/3)
+  const double sn = 0.86602540378443864676;
+  const cd t = cadd(a1, a2), d = csub(a1, a2);
+  const cd m = mk(a0.x - 0.5 * t.x, a0.y - 0.5 * t.y), js = mk(sn * d.y, -sn * d.x);   // js = -i sn d
+  a0 = cadd(a0, t);
+  a1 = cadd(m, js);
+  a2 = csub(m, js);
+}
+__device__ __forceinline__ void bfly5(cd (&a)[5]) {
+  const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;   // cos(2 pi/5), cos(4 pi/5)
+  const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;    // sin(2 pi/5), sin(4 pi/5)
+  const cd t1 = cadd(a[1], a[4]), t2 = cadd(a[2], a[3]), d1 = csub(a[1], a[4]), d2 = csub(a[2], a[3]);
+  const cd m1 = mk(a[0].x + c1 * t1.x + c2 * t2.x, a[0].y + c1 * t1.y + c2 * t2.y);
+  const cd m2 = mk(a[0].x + c2 * t1.x + c1 * t2.x, a[0].y + c2 * t1.y + c1 * t2.y);
+  const cd n1 = mk(s1 * d1.x + s2 * d2.x, s1 * d1.y + s2 * d2.y);
+  const cd n2 = mk(s2 * d1.x - s1 * d2.x, s2 * d1.y - s1 * d2.y);
+  a[0] = cadd(a[0], cadd(t1, t2));
+  a[1] = mk(m1.x + n1.y, m1.y - n1.x);                   // m1 - i n1
+  a[4] = mk(m1.x - n1.y, m1.y + n1.x);                   // m1 + i n1
+  a[2] = mk(m2.x + n2.y, m2.y - n2.x);
+  a[3] = mk(m2.x - n2.y, m2.y + n2.x);
+}
+
 // ---------------------------------------------------------------------------------------------
-// the power-of-two core
+// the mixed-radix core (lengths blk * 2^a 3^b 5^c, blk = 16, 8 or 4)
 // ---------------------------------------------------------------------------------------------
-// Pass schedule for an m = 2^log2m point sub-transform and the layout of its per-pass twiddle tables:
-// pass p has span L[p], radix r[p], q = L/r butterflies per block, and q table entries w_L^j (j < q)
+// Pass schedule for an m-point sub-transform and the layout of its per-pass twiddle tables: the passes
+// (decimation in frequency, span L[p], radix r[p] in {2, 3, 4, 5, 8}) take the span from m down to
+// contiguous blocks of `blk` points (16, else 8, else 4 - the largest that divides m), which one thread
+// finishes in registers.  Pass p has q = L/r butterflies per block and q table entries w_L^j (j < q)
 // starting at tw_off[p]; the higher powers w_L^{2j} .. w_L^{(r-1)j} are formed in float64 registers
-// (six complex products for radix 8) instead of being loaded - the pass is bound by load latency,
-// not by the FP64 pipe.
+// instead of being loaded.  n_pass < 0: m has a prime factor other than 2, 3, 5 (or is not a multiple of 4).
 struct PassPlan {
-  int n_pass, total;
+  int n_pass, total, blk;
   int L[kMaxPasses], r[kMaxPasses], tw_off[kMaxPasses];
+  int sh[kMaxPasses];       // log2 of (L / r) / blk, the block-index weight of pass p's digit, or -1 if not a power of two
 };
-__host__ __device__ inline void plan_add(PassPlan& pp, int L, int r) {
+__host__ __device__ inline void plan_add(PassPlan& pp, int& L, int r) {
+  if (pp.n_pass < 0 || pp.n_pass >= kMaxPasses) { pp.n_pass = -1; return; }
   pp.L[pp.n_pass] = L;
   pp.r[pp.n_pass] = r;
   pp.tw_off[pp.n_pass] = pp.total;
   pp.total += L / r;
+  L /= r;
+  const int stride = L / pp.blk;
+  int sh = -1;
+  if ((stride & (stride - 1)) == 0)
+    for (sh = 0; (1 << sh) < stride; ++sh) {}
+  pp.sh[pp.n_pass] = sh;
   ++pp.n_pass;
 }
-__host__ __device__ inline PassPlan make_passes(int log2m) {
+__host__ __device__ inline PassPlan make_passes(int m) {
   PassPlan pp;
   pp.n_pass = 0;
   pp.total = 0;
-  int L = 1 << log2m;
-  const int rem = (log2m - 4) % 3;
-  if (rem) { plan_add(pp, L, 1 << rem); L >>= rem; }
-  while (L > kBlk) { plan_add(pp, L, 8); L >>= 3; }
+  pp.blk = m % 16 == 0 ? 16 : (m % 8 == 0 ? 8 : (m % 4 == 0 ? 4 : 0));
+  if (m <= 0 || pp.blk == 0) { pp.n_pass = -1; return pp; }
+  int x = m / pp.blk, L = m, twos = 0;
+  while (x % 2 == 0) { x /= 2; ++twos; }
+  if (twos % 3) plan_add(pp, L, 1 << (twos % 3));        // one leading radix-2 or radix-4 pass, then radix 8
+  for (int i = 0; i < twos / 3; ++i) plan_add(pp, L, 8);
+  while (x % 5 == 0) { x /= 5; plan_add(pp, L, 5); }
+  while (x % 3 == 0) { x /= 3; plan_add(pp, L, 3); }
+  if (x != 1) pp.n_pass = -1;
   return pp;
 }
 
 // Geometry of one launch: transform length n_fft = m * R.
 struct FftGeom {
-  int m, log2m, R, n_fft;
+  int m, R, n_fft;
   const double2* tw;        // w_n^j, j < n_fft (load-time split of long transforms)
   const double2* pass_tw;   // per-pass tables
   PassPlan pp;
 };
 
-template <int RADIX>
-__device__ __forceinline__ void smem_butterfly(sc* __restrict__ s, int b, int q, int qs,
-                                               const double2* __restrict__ tab) {
-  const int j = b & (q - 1);
-  const int p0 = phys((b - j) * RADIX + j);            // (b / q) * L + j
+// kPow2: q is a power of two and a multiple of 16 (every pass of a power-of-two length with 16-point blocks):
+// mask instead of division, and a constant leg stride in the padded storage.
+template <int RADIX, bool kPow2>
+__device__ __forceinline__ void smem_butterfly(sc* __restrict__ s, int b, int q, const double2* __restrict__ tab) {
+  const int j = kPow2 ? (b & (q - 1)) : b % q;
+  const int p0 = (b - j) * RADIX + j;                         // (b / q) * L + j; legs are q apart
   const double2 t = __ldg(tab + j);
+  const int pp0 = phys(p0), qs = q + (q >> 4);
   cd a[RADIX];
 #pragma unroll
-  for (int i = 0; i < RADIX; ++i) a[i] = to_cd(s[p0 + i * qs]);
+  for (int i = 0; i < RADIX; ++i) a[i] = to_cd(s[kPow2 ? pp0 + i * qs : phys(p0 + i * q)]);
   const cd w1 = mk(t.x, t.y);
   if (RADIX == 2) {
     bfly2(a[0], a[1]);
     a[1] = cmul(a[1], w1);
+  }
+  if (RADIX == 3) {
+    bfly3(a[0], a[1], a[2]);
+    a[1] = cmul(a[1], w1);
+    a[2] = cmul(a[2], cmul(w1, w1));
   }
   if (RADIX == 4) {
     bfly4(a[0], a[1], a[2], a[3]);
@@ -172,6 +218,14 @@ __device__ __forceinline__ void smem_butterfly(sc* __restrict__ s, int b, int q,
     a[1] = cmul(a[1], w1);
     a[2] = cmul(a[2], w2);
     a[3] = cmul(a[3], cmul(w2, w1));
+  }
+  if (RADIX == 5) {
+    bfly5(reinterpret_cast<cd(&)[5]>(a));
+    const cd w2 = cmul(w1, w1);
+    a[1] = cmul(a[1], w1);
+    a[2] = cmul(a[2], w2);
+    a[3] = cmul(a[3], cmul(w2, w1));
+    a[4] = cmul(a[4], cmul(w2, w2));
   }
   if (RADIX == 8) {
     bfly8(reinterpret_cast<cd(&)[8]>(a));
@@ -185,22 +239,26 @@ __device__ __forceinline__ void smem_butterfly(sc* __restrict__ s, int b, int q,
     a[7] = cmul(a[7], cmul(w4, w3));
   }
 #pragma unroll
-  for (int i = 0; i < RADIX; ++i) s[p0 + i * qs] = to_sc(a[i]);
+  for (int i = 0; i < RADIX; ++i) s[kPow2 ? pp0 + i * qs : phys(p0 + i * q)] = to_sc(a[i]);
 }
 
-template <int RADIX>
-__device__ __forceinline__ void smem_pass(sc* __restrict__ s, int m, int L, const double2* __restrict__ tab) {
-  const int q = L / RADIX;
-  const int qs = q + (q >> 4);                         // leg stride in padded storage (q is a multiple of 16)
+template <int RADIX, bool kPow2>
+__device__ __forceinline__ void smem_pass_impl(sc* __restrict__ s, int m, int q, const double2* __restrict__ tab) {
   const int n_bfly = m / RADIX, step = blockDim.x;
   if (n_bfly % step == 0) {                            // uniform trip count: no exit test between iterations
     const int per_thread = n_bfly / step;
 #pragma unroll kFftUnroll
-    for (int i = 0; i < per_thread; ++i) smem_butterfly<RADIX>(s, threadIdx.x + i * step, q, qs, tab);
+    for (int i = 0; i < per_thread; ++i) smem_butterfly<RADIX, kPow2>(s, threadIdx.x + i * step, q, tab);
   } else {
-    for (int b = threadIdx.x; b < n_bfly; b += step) smem_butterfly<RADIX>(s, b, q, qs, tab);
+    for (int b = threadIdx.x; b < n_bfly; b += step) smem_butterfly<RADIX, kPow2>(s, b, q, tab);
   }
   __syncthreads();
+}
+template <int RADIX>
+__device__ __forceinline__ void smem_pass(sc* __restrict__ s, int m, int L, const double2* __restrict__ tab) {
+  const int q = L / RADIX;
+  if (RADIX != 3 && RADIX != 5 && (q & (q - 1)) == 0 && (q & 15) == 0) smem_pass_impl<RADIX, true>(s, m, q, tab);
+  else smem_pass_impl<RADIX, false>(s, m, q, tab);
 }
 
 __device__ void fft_smem_passes(sc* __restrict__ s, const FftGeom& g) {
@@ -210,7 +268,9 @@ __device__ void fft_smem_passes(sc* __restrict__ s, const FftGeom& g) {
       const double2* tab = g.pass_tw + g.pp.tw_off[p];
       if (g.pp.r[p] == 8) smem_pass<8>(s, g.m, g.pp.L[p], tab);
       else if (g.pp.r[p] == 4) smem_pass<4>(s, g.m, g.pp.L[p], tab);
-      else smem_pass<2>(s, g.m, g.pp.L[p], tab);
+      else if (g.pp.r[p] == 2) smem_pass<2>(s, g.m, g.pp.L[p], tab);
+      else if (g.pp.r[p] == 5) smem_pass<5>(s, g.m, g.pp.L[p], tab);
+      else smem_pass<3>(s, g.m, g.pp.L[p], tab);
     }
   }
 }
@@ -244,21 +304,33 @@ __device__ __forceinline__ void fft16_registers(cd (&x)[kBlk]) {
   for (int blk = 0; blk < 4; ++blk) bfly4(x[4 * blk], x[4 * blk + 1], x[4 * blk + 2], x[4 * blk + 3]);
 }
 
-// frequency (within the m-point sub-transform) of element 0 of block b; element e adds (m/16) * rev(e)
+// Frequency (within the m-point sub-transform) of element 0 of block b; register e of the finished block
+// adds (m / blk) * rev(e).  The block index is a mixed-radix number, most significant digit = first pass;
+// that digit is the LEAST significant digit of the frequency.
 __device__ __forceinline__ int block_base_frequency(int b, const FftGeom& g) {
-  int bits = g.log2m - 4;      // bits of the block index, consumed most-significant first, one digit per pass
-  int f = 0, shift = 0;
+  int stride = g.m / g.pp.blk, f = 0, weight = 1;
 #pragma unroll
   for (int p = 0; p < kMaxPasses; ++p) {
     if (p < g.pp.n_pass) {
-      const int w = g.pp.r[p] == 8 ? 3 : (g.pp.r[p] == 4 ? 2 : 1);
-      bits -= w;
-      f += ((b >> bits) & (g.pp.r[p] - 1)) << shift;
-      shift += w;
+      stride /= g.pp.r[p];                             // uniform, from the constant bank
+      const int d = g.pp.sh[p] >= 0 ? (b >> g.pp.sh[p]) : b / stride;
+      b -= d * stride;
+      f += d * weight;
+      weight *= g.pp.r[p];
     }
   }
   return f;
 }
+
+// Finish one contiguous block held in registers; rev(e) = block-local frequency index of register e.
+template <int BLK>
+__device__ __forceinline__ void finish_block(cd (&x)[BLK]) {
+  if constexpr (BLK == 16) fft16_registers(x);
+  if constexpr (BLK == 8) bfly8(x);
+  if constexpr (BLK == 4) bfly4(x[0], x[1], x[2], x[3]);
+}
+template <int BLK>
+__device__ __forceinline__ constexpr int block_rev(int e) { return BLK == 16 ? (e >> 2) + 4 * (e & 3) : e; }
 
 // output r of a 4-point forward DFT: sum_j x_j (-i)^{jr}
 __device__ __forceinline__ cd dif4(cd x0, cd x1, cd x2, cd x3, int r) {
@@ -266,6 +338,39 @@ __device__ __forceinline__ cd dif4(cd x0, cd x1, cd x2, cd x3, int r) {
   if (r == 2) return csub(cadd(x0, x2), cadd(x1, x3));
   const cd d = mul_neg_i(csub(x1, x3));               // -i (x1 - x3)
   return r == 1 ? cadd(csub(x0, x2), d) : csub(csub(x0, x2), d);
+}
+
+// Radix-RR split for small odd-ish RR (frame counts like 20 000 = 5 x 4000): the RR twiddles w_RR^{jr} live in
+// registers and two outputs (2 RR loads) are in flight per thread.
+template <int RR, class Fetch>
+__device__ void load_split_small(sc* __restrict__ s, const Fetch& fetch, const FftGeom& g, int r) {
+  double2 w[RR];
+#pragma unroll
+  for (int j = 0; j < RR; ++j) w[j] = __ldg(g.tw + ((j * r) % RR) * g.m);
+  auto residue = [&](const cd (&x)[RR], int t) -> sc {
+    cd acc = x[0];
+#pragma unroll
+    for (int j = 1; j < RR; ++j) acc = cadd(acc, r ? cmul(x[j], w[j]) : x[j]);
+    return to_sc(r ? cmul(acc, __ldg(g.tw + (int64_t)t * r)) : acc);
+  };
+  const int step = blockDim.x;
+  int t = threadIdx.x;
+  for (; t + step < g.m; t += 2 * step) {
+    cd x0[RR], x1[RR];
+#pragma unroll
+    for (int j = 0; j < RR; ++j) {
+      x0[j] = fetch(t + j * g.m);
+      x1[j] = fetch(t + step + j * g.m);
+    }
+    s[phys(t)] = residue(x0, t);
+    s[phys(t + step)] = residue(x1, t + step);
+  }
+  for (; t < g.m; t += step) {
+    cd x0[RR];
+#pragma unroll
+    for (int j = 0; j < RR; ++j) x0[j] = fetch(t + j * g.m);
+    s[phys(t)] = residue(x0, t);
+  }
 }
 
 // Fill shared memory with sub-sequence r of the radix-R split of fetch(0..n_fft) (R == 1: plain copy).
@@ -351,11 +456,15 @@ __device__ void load_column(sc* __restrict__ s, const Fetch& fetch, const FftGeo
     }
     return;
   }
+  if (g.R == 3) return load_split_small<3>(s, fetch, g, r);
+  if (g.R == 5) return load_split_small<5>(s, fetch, g, r);
+  if (g.R == 6) return load_split_small<6>(s, fetch, g, r);
+  if (g.R == 10) return load_split_small<10>(s, fetch, g, r);
   for (int t = threadIdx.x; t < g.m; t += step) {     // general R: sum_j x[t + j m] w_R^{jr}, times w_n^{tr}
     cd acc = mk(0.0, 0.0);
     for (int j = 0; j < g.R; ++j) {
       cd x = fetch(t + j * g.m);
-      const int wi = ((j * r) & (g.R - 1)) * g.m;                      // w_R^{jr} = w_n^{(jr mod R) m}
+      const int wi = ((j * r) % g.R) * g.m;                            // w_R^{jr} = w_n^{(jr mod R) m}
       acc = cadd(acc, wi ? cmul(x, __ldg(g.tw + wi)) : x);
     }
     s[phys(t)] = to_sc(r ? cmul(acc, __ldg(g.tw + (int64_t)t * r)) : acc);   // w_n^{tr}, t r < n
@@ -364,22 +473,25 @@ __device__ void load_column(sc* __restrict__ s, const Fetch& fetch, const FftGeo
 
 // Transform the column in shared memory and feed every (slot, frequency, value) to the sink.
 // slot = padded in-place position, owned by the same thread on every call with the same geometry.
+template <int BLK, class Sink>
+__device__ __forceinline__ void finish_and_emit(sc* __restrict__ s, const FftGeom& g, int r, Sink& sink) {
+  const int n_blocks = g.m / BLK;
+  for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) {
+    cd x[BLK];
+#pragma unroll
+    for (int e = 0; e < BLK; ++e) x[e] = to_cd(s[phys(b * BLK + e)]);
+    finish_block<BLK>(x);
+    const int f0 = block_base_frequency(b, g);
+#pragma unroll
+    for (int e = 0; e < BLK; ++e) sink(phys(b * BLK + e), (f0 + n_blocks * block_rev<BLK>(e)) * g.R + r, x[e]);
+  }
+}
 template <class Sink>
 __device__ void transform_and_emit(sc* __restrict__ s, const FftGeom& g, int r, Sink& sink) {
   fft_smem_passes(s, g);
-  const int n_blocks = g.m >> 4, fstep = g.m >> 4;
-  for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) {
-    cd x[kBlk];
-#pragma unroll
-    for (int e = 0; e < kBlk; ++e) x[e] = to_cd(s[b * (kBlk + 1) + e]);
-    fft16_registers(x);
-    const int f0 = block_base_frequency(b, g);
-#pragma unroll
-    for (int e = 0; e < kBlk; ++e) {
-      const int rev = (e >> 2) + 4 * (e & 3);
-      sink(b * (kBlk + 1) + e, (f0 + fstep * rev) * g.R + r, x[e]);
-    }
-  }
+  if (g.pp.blk == 16) finish_and_emit<16>(s, g, r, sink);
+  else if (g.pp.blk == 8) finish_and_emit<8>(s, g, r, sink);
+  else finish_and_emit<4>(s, g, r, sink);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -492,20 +604,27 @@ __device__ __forceinline__ void column_rows(const SedArgs& a, int g, int k, int 
 }
 
 // write the intensities accumulated per slot (same thread -> slot mapping as transform_and_emit)
-__device__ void flush_accumulator(const float* __restrict__ s_acc, float* __restrict__ o, int64_t fstride, int n_valid,
-                                  const FftGeom& g, int r) {
-  const int n_blocks = g.m >> 4, fstep = g.m >> 4;
+template <int BLK>
+__device__ __forceinline__ void flush_blocks(const float* __restrict__ s_acc, float* __restrict__ o, int64_t fstride,
+                                             int n_valid, const FftGeom& g, int r) {
+  const int n_blocks = g.m / BLK;
   for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) {
     const int f0 = block_base_frequency(b, g);
 #pragma unroll
-    for (int e = 0; e < kBlk; ++e) {
-      const int f = (f0 + fstep * ((e >> 2) + 4 * (e & 3))) * g.R + r;
-      if (f < n_valid) o[(int64_t)f * fstride] = s_acc[b * (kBlk + 1) + e];
+    for (int e = 0; e < BLK; ++e) {
+      const int f = (f0 + n_blocks * block_rev<BLK>(e)) * g.R + r;
+      if (f < n_valid) o[(int64_t)f * fstride] = s_acc[phys(b * BLK + e)];
     }
   }
 }
+__device__ void flush_accumulator(const float* __restrict__ s_acc, float* __restrict__ o, int64_t fstride, int n_valid,
+                                  const FftGeom& g, int r) {
+  if (g.pp.blk == 16) flush_blocks<16>(s_acc, o, fstride, n_valid, g, r);
+  else if (g.pp.blk == 8) flush_blocks<8>(s_acc, o, fstride, n_valid, g, r);
+  else flush_blocks<4>(s_acc, o, fstride, n_valid, g, r);
+}
 
-// Power-of-two n_t: P -> result in one kernel.
+// Direct lengths (n_t = R * m with a mixed-radix m): P -> result in one kernel.
 template <int kMode>
 __global__ void __launch_bounds__(kFftThreads, kFftMinCtas) fft_sed_kernel(SedArgs a, FftGeom g) {
   extern __shared__ sc s_data[];
@@ -644,45 +763,42 @@ __global__ void chirp_kernel(int64_t n, int64_t M, double2* __restrict__ chirp, 
   padded[t] = val;
 }
 
-static bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
-static bool direct_length(int64_t n) { return is_pow2(n) && n >= kBlk; }
-
 static int64_t bluestein_length(int64_t n) {
   int64_t m = 32;
   while (m < 2 * n - 1) m <<= 1;
   return m;
 }
 
+// n_fft = R * m: the largest m <= max_points that the mixed-radix core can transform (smallest R).
+// Returns 0 when there is none (a large prime factor, or n not a multiple of 4): Bluestein takes over.
 static int64_t sub_length(int64_t n_fft, int* R_out) {
   static const int64_t max_points = []() -> int64_t {     // tuning knob, see profiles/
     const char* env = getenv("PSA_FFT_MAX_POINTS");
     int64_t v = env ? atoll(env) : kDefaultSmemPoints;
-    if (v < 64 || v > kMaxSmemPoints || (v & (v - 1))) v = kDefaultSmemPoints;
+    if (v < 64 || v > kMaxSmemPoints) v = kDefaultSmemPoints;
     return v;
   }();
-  int64_t m = n_fft;
-  int R = 1;
-  while (m > max_points) { m >>= 1; R <<= 1; }
-  if (R_out) *R_out = R;
-  return m;
+  for (int64_t R = (n_fft + max_points - 1) / max_points; R <= 256 && R <= n_fft; ++R) {
+    if (n_fft % R) continue;
+    const int64_t m = n_fft / R;
+    if (m <= max_points && make_passes((int)m).n_pass >= 0) {
+      if (R_out) *R_out = (int)R;
+      return m;
+    }
+  }
+  return 0;
 }
+static bool direct_length(int64_t n) { return n >= 4 && sub_length(n, nullptr) > 0; }
 
-static int ilog2(int64_t v) {
-  int l = 0;
-  while (((int64_t)1 << l) < v) ++l;
-  return l;
-}
-
-static int64_t pass_table_entries(int64_t n_fft) { return make_passes(ilog2(sub_length(n_fft, nullptr))).total; }
+static int64_t pass_table_entries(int64_t n_fft) { return make_passes((int)sub_length(n_fft, nullptr)).total; }
 
 static FftGeom make_geom(int64_t n_fft, const double2* tw) {   // tw = start of the plan: [tw | pass tables | ...]
   FftGeom g;
   g.m = (int)sub_length(n_fft, &g.R);
   g.n_fft = (int)n_fft;
-  g.log2m = ilog2(g.m);
   g.tw = tw;
   g.pass_tw = tw + n_fft;
-  g.pp = make_passes(g.log2m);
+  g.pp = make_passes(g.m);
   return g;
 }
 
@@ -699,7 +815,7 @@ static int allow_smem(K kernel, size_t bytes) {
 
 static int build_tables(int64_t n_fft, double2* tw, cudaStream_t s) {
   twiddle_kernel<<<(unsigned)((n_fft + 255) / 256), 256, 0, s>>>(n_fft, tw);
-  const PassPlan pp = make_passes(ilog2(sub_length(n_fft, nullptr)));
+  const PassPlan pp = make_passes((int)sub_length(n_fft, nullptr));
   double2* pass = tw + n_fft;
   for (int p = 0; p < pp.n_pass; ++p) {
     const int entries = pp.L[p] / pp.r[p];

@@ -206,9 +206,12 @@ def test_fft_incoherent(eng, n_t):
     np.testing.assert_allclose(out.cpu().numpy(), want, rtol=2e-5, atol=1e-6 * want.max())
 
 
-@pytest.mark.parametrize("n_t", [2, 7, 16, 250, 1000, 3001, 8191, 10000, 20000])
+# 4 * 2^a 3^b 5^c -> mixed-radix core (final blocks of 16 / 8 / 4 points, load-time split by R = 3, 5, 25 ...);
+# anything else (odd lengths, a large prime factor) -> Bluestein
+@pytest.mark.parametrize("n_t", [2, 4, 7, 8, 12, 16, 20, 28, 48, 60, 80, 250, 360, 1000, 1200, 3000, 3001, 5000, 8191,
+                                 10000, 12288, 20000, 50000])
 def test_fft_any_length_bluestein(eng, n_t):
-    """Frame counts that are not a power of two (the reference accepts any n_t) go through Bluestein."""
+    """Frame counts that are not a power of two (the reference accepts any n_t): mixed radix or Bluestein."""
     rng = np.random.default_rng(n_t)
     n_k, ldp = 2, -(-n_t // 4) * 4
     P = np.zeros((2 * n_k, 3, ldp), np.float32)
