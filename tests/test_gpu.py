@@ -454,9 +454,10 @@ def test_odd_frame_count_matches_reference(gold_si):
 
 
 # ------------------------------------------------------------------ medium size: three-distance parity report
-def test_three_distance_parity_medium():
+@pytest.mark.parametrize("n_frames", [2048, 3000])      # power of two / mixed radix (8-point blocks, radix 5 and 3 passes)
+def test_three_distance_parity_medium(n_frames):
     from psa_b200 import SEDCalculator
-    spec = synth.si_spec("mid", n_cells=4, n_frames=2048, seed=21)
+    spec = synth.si_spec("mid", n_cells=4, n_frames=n_frames, seed=21)
     traj = spec.trajectory()
     calc = SEDCalculator(traj, *spec.cells)
     for direction in ([1, 0, 0], [1, 1, 0]):
