@@ -367,6 +367,24 @@ def main():
     e2e = None
     if not args.no_e2e:
         d2h = [0]
+        # N > 1: every rank uploads its own 1/N of the frames (pinned) over its own PCIe link
+        ingest, local_rows = "broadcast", None
+        if world > 1:
+            f0, f1 = pdist.shard_range(spec.n_frames, rank, world)
+            if not share or rank == 0:
+                ingest = "sliced"
+                local_rows = (traj.positions[f0:f1], traj.velocities[f0:f1])
+            elif f0 % 256 == 0:                              # synthetic frames are generated in blocks of 256
+                ingest = "sliced"
+                rows_shape = (f1 - f0, spec.n_atoms, 3)
+                lp = torch.empty(rows_shape, dtype=torch.float32, pin_memory=True).numpy()
+                lv = torch.empty(rows_shape, dtype=torch.float32, pin_memory=True).numpy()
+                spec.frames(f0, f1, out_pos=lp, out_vel=lv, threads=min(16, os.cpu_count() or 8))
+                local_rows = (lp, lv)
+            flag = torch.tensor([1 if ingest == "sliced" else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                ingest, local_rows = "broadcast", None
 
         def step_e2e():
             calc.release_device_memory()
@@ -379,7 +397,7 @@ def main():
                     else:
                         res = calc.calculate(mags, vecs, **kw)
                 else:
-                    res = pdist.calculate_sharded(calc, mags, vecs, **kw)
+                    res = pdist.calculate_sharded(calc, mags, vecs, ingest=ingest, local_rows=local_rows, **kw)
                 if res is not None:
                     res_bytes += res.sed.nbytes + (res.phase.nbytes if res.phase is not None else 0)
             d2h[0] = res_bytes
@@ -405,7 +423,9 @@ def main():
                "steps": n_e2e, "h2d_bytes_per_step": int(2 * traj.positions.nbytes),
                "d2h_bytes_per_step": int(d2h[0]),
                "path": "SEDCalculator.calculate on pinned host arrays" if world == 1 else
-                       "psa_b200.dist.calculate_sharded: rank-0 upload+ingest, NCCL broadcast, k-sharded compute, gather, D2H"}
+                       ("psa_b200.dist.calculate_sharded(ingest='sliced'): every rank uploads 1/N of the frames, running-sum "
+                        "mean chain + all-gather of the digit planes, k-sharded compute, gather, D2H" if ingest == "sliced" else
+                        "psa_b200.dist.calculate_sharded: rank-0 upload+ingest, NCCL broadcast, k-sharded compute, gather, D2H")}
 
     # ---------------- batched iSED (configs that name it: C5's 64 (k, omega) points, split over the ranks)
     ised = None

@@ -59,6 +59,20 @@ int psa_mean_positions(const float* pos, int64_t n_t, int64_t n_a, float* mean, 
 int psa_digitize(const float* data, const float* mean, const int32_t* idx, int64_t n_t, int64_t n_a,
                  int64_t n_sel, int64_t pitch, int8_t* dig, int32_t* expo, void* stream);
 
+/* The two ingest steps on a contiguous range of frames, for a trajectory whose frames are spread over several
+ * GPUs (each rank uploads 1/N of the frames over its own PCIe link):
+ *   psa_mean_accumulate: out[c] = (acc_in ? acc_in[c] : 0) (+) pos[0][c] (+) ... (+) pos[n_rows-1][c] in float32, in
+ *     row order, then / (float)divide_by when divide_by > 0.  Chained over the ranks in frame order this is the
+ *     same sequence of additions as psa_mean_positions, i.e. np.mean(..., axis=0, dtype=float32) bit for bit
+ *     (reference: sed_calculator.py:205).  acc_in may alias out.
+ *   psa_digitize_rows: psa_digitize for rows [t0, t0 + n_rows) of an n_t_total-frame trajectory; `data` points at
+ *     row t0, dig / expo are the full-size outputs. */
+int psa_mean_accumulate(const float* pos, int64_t n_rows, int64_t n_atoms, const float* acc_in, int64_t divide_by,
+                        float* out, void* stream);
+int psa_digitize_rows(const float* data, const float* mean, const int32_t* idx, int64_t n_rows, int64_t n_atoms,
+                      int64_t n_sel, int64_t pitch, int8_t* dig, int32_t* expo, int64_t n_t_total, int64_t t0,
+                      void* stream);
+
 /* Phase table exp(+i k.r) as digit planes.  theta = fma(k2,r2,fma(k1,r1,k0*r0)) in float32, then
  * correctly rounded float32 cos/sin (reference: sed_calculator.py:78, np.exp(1j*np.dot(k, r.T))).
  *   kvecs [n_k][3] float32   mean [n_a][3] float32   idx [n_sel] or NULL

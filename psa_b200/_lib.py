@@ -49,6 +49,9 @@ _SIGNATURES = {
                                 c_void_p, c_void_p]),
     "psa_disp_moments": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "psa_absmax": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "psa_mean_accumulate": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "psa_digitize_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                                  c_int64, c_int64, c_void_p]),
     "psa_copy_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
 }
 

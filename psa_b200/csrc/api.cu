@@ -62,6 +62,25 @@ int psa_digitize(const float* data, const float* mean, const int32_t* idx, int64
   return launch_digitize(data, mean, idx, n_t, n_a, n_sel, pitch, dig, expo, as_stream(stream));
 }
 
+int psa_mean_accumulate(const float* pos, int64_t n_rows, int64_t n_a, const float* acc_in, int64_t divide_by,
+                        float* out, void* stream) {
+  PSA_REQUIRE(n_rows >= 0 && n_a >= 0 && divide_by >= 0, "psa_mean_accumulate: negative extent");
+  PSA_REQUIRE(n_a == 0 || (out && (pos || n_rows == 0)), "psa_mean_accumulate: null pointer");
+  return launch_mean_accumulate(pos, n_rows, n_a, acc_in, divide_by, out, as_stream(stream));
+}
+
+int psa_digitize_rows(const float* data, const float* mean, const int32_t* idx, int64_t n_rows, int64_t n_a,
+                      int64_t n_sel, int64_t pitch, int8_t* dig, int32_t* expo, int64_t n_t_total, int64_t t0,
+                      void* stream) {
+  PSA_REQUIRE(dig && expo && (data || n_rows == 0), "psa_digitize_rows: null pointer");
+  PSA_REQUIRE(n_rows >= 0 && t0 >= 0 && t0 + n_rows <= n_t_total && n_a > 0 && n_sel > 0,
+              "psa_digitize_rows: bad extent (rows [%lld, %lld) of %lld frames)", (long long)t0,
+              (long long)(t0 + n_rows), (long long)n_t_total);
+  PSA_REQUIRE(idx != nullptr || n_sel == n_a, "psa_digitize_rows: n_sel must equal n_a when idx is NULL");
+  PSA_REQUIRE(pitch >= n_sel && pitch % 64 == 0, "psa_digitize_rows: pitch must be a multiple of 64 and >= n_sel");
+  return launch_digitize_rows(data, mean, idx, n_rows, n_a, n_sel, pitch, dig, expo, n_t_total, t0, as_stream(stream));
+}
+
 int psa_phase_digits(const float* kvecs, int64_t n_k, const float* mean, const int32_t* idx, int64_t n_sel,
                      int64_t pitch, int64_t rows_alloc, int8_t* adig, void* stream) {
   PSA_REQUIRE(kvecs && mean && adig, "psa_phase_digits: null pointer");

@@ -62,6 +62,11 @@ inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 // device-side kernels' host launchers (one per .cu file)
 int launch_mean_positions(const float* pos, int64_t n_t, int64_t n_a, float* mean, cudaStream_t s);
+int launch_mean_accumulate(const float* pos, int64_t n_t, int64_t n_a, const float* acc_in, int64_t divide_by, float* mean,
+                           cudaStream_t s);
+int launch_digitize_rows(const float* data, const float* mean, const int32_t* idx, int64_t n_rows, int64_t n_a,
+                         int64_t n_sel, int64_t pitch, int8_t* dig, int32_t* expo, int64_t n_t_total, int64_t t0,
+                         cudaStream_t s);
 int launch_digitize(const float* data, const float* mean, const int32_t* idx, int64_t n_t, int64_t n_a,
                     int64_t n_sel, int64_t pitch, int8_t* dig, int32_t* expo, cudaStream_t s);
 int launch_phase_digits(const float* kvecs, int64_t n_k, const float* mean, const int32_t* idx,

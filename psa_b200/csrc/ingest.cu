@@ -31,8 +31,11 @@ constexpr int kMeanThreads = 512;
 constexpr int kMeanPerThread = kMeanRows * kMeanCols / kMeanThreads;   // loads in flight per thread
 constexpr int kMeanConsumers = kMeanCols / 32;
 
+// out = (acc_in ? acc_in : 0) (+) the rows in order, then / divisor when divisor > 0 (a multi-GPU ingest
+// passes the running sums of a frame slice from rank to rank: the additions stay in frame order).
 __global__ void __launch_bounds__(kMeanThreads) mean_positions_kernel(const float* __restrict__ pos, int64_t n_t,
-                                                                      int64_t n_cols, float* __restrict__ mean) {
+                                                                      int64_t n_cols, const float* acc_in, float divisor,
+                                                                      float* mean) {
   extern __shared__ float mean_smem[];
   float (*tile)[kMeanRows][kMeanCols] = reinterpret_cast<float (*)[kMeanRows][kMeanCols]>(mean_smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -55,7 +58,8 @@ __global__ void __launch_bounds__(kMeanThreads) mean_positions_kernel(const floa
   };
 
   float acc = 0.0f;
-  fetch(0);
+  if (acc_in != nullptr && warp < kMeanConsumers && col0 + warp * 32 + lane < n_cols) acc = acc_in[col0 + warp * 32 + lane];
+  if (n_tiles > 0) fetch(0);
   for (int64_t it = 0; it < n_tiles; ++it) {
     const int buf = (int)(it & 1);
 #pragma unroll
@@ -77,7 +81,7 @@ __global__ void __launch_bounds__(kMeanThreads) mean_positions_kernel(const floa
   }
   if (warp < kMeanConsumers) {
     const int64_t col = col0 + warp * 32 + lane;
-    if (col < n_cols) mean[col] = __fdiv_rn(acc, (float)n_t);
+    if (col < n_cols) mean[col] = divisor > 0.f ? __fdiv_rn(acc, divisor) : acc;
   }
 }
 
@@ -129,7 +133,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 __global__ void __launch_bounds__(kTmaThreads) mean_positions_tma_kernel(const __grid_constant__ CUtensorMap map, int n_t,
-                                                                         int64_t n_cols, float* __restrict__ mean) {
+                                                                         int64_t n_cols, const float* acc_in, float divisor,
+                                                                         float* mean) {
   extern __shared__ __align__(128) float tma_tiles[];        // [stage][row][col]
   __shared__ uint64_t full_bar[kTmaStages], empty_bar[kTmaStages];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(kTmaThreads) mean_positions_tma_kernel(const _
   }
 
   const int c = warp * 32 + lane;
-  float acc = 0.0f;
+  float acc = (acc_in != nullptr && col0 + c < n_cols) ? acc_in[col0 + c] : 0.0f;
   for (int i = 0; i < n_tiles; ++i) {
     const int s = i % kTmaStages;
     mbar_wait(&full_bar[s], (i / kTmaStages) & 1);
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(kTmaThreads) mean_positions_tma_kernel(const _
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);                // this warp is done reading the stage
   }
-  if (col0 + c < n_cols) mean[col0 + c] = __fdiv_rn(acc, (float)n_t);
+  if (col0 + c < n_cols) mean[col0 + c] = divisor > 0.f ? __fdiv_rn(acc, divisor) : acc;
 }
 
 static bool mean_use_tma(const float* pos, int64_t n_t, int64_t n_cols) {
@@ -189,9 +194,15 @@ static bool mean_use_tma(const float* pos, int64_t n_t, int64_t n_cols) {
 }
 
 int launch_mean_positions(const float* pos, int64_t n_t, int64_t n_a, float* mean, cudaStream_t s) {
+  return launch_mean_accumulate(pos, n_t, n_a, nullptr, n_t, mean, s);
+}
+
+int launch_mean_accumulate(const float* pos, int64_t n_t, int64_t n_a, const float* acc_in, int64_t divide_by, float* mean,
+                           cudaStream_t s) {
   int64_t n_cols = n_a * 3;
   if (n_cols == 0) return PSA_OK;
-  if (mean_use_tma(pos, n_t, n_cols)) {
+  const float divisor = divide_by > 0 ? (float)divide_by : 0.f;
+  if (n_t > 0 && mean_use_tma(pos, n_t, n_cols)) {
     CUtensorMap map;
     cuuint64_t dims[2] = {(cuuint64_t)n_cols, (cuuint64_t)n_t};
     cuuint64_t strides[1] = {(cuuint64_t)n_cols * sizeof(float)};
@@ -208,13 +219,13 @@ int launch_mean_positions(const float* pos, int64_t n_t, int64_t n_a, float* mea
     constexpr int smem = kTmaStages * (int)kTmaStageBytes;
     PSA_CUDA(cudaFuncSetAttribute(mean_positions_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t blocks = (n_cols + kTmaCols - 1) / kTmaCols;
-    mean_positions_tma_kernel<<<(unsigned)blocks, kTmaThreads, smem, s>>>(map, (int)n_t, n_cols, mean);
+    mean_positions_tma_kernel<<<(unsigned)blocks, kTmaThreads, smem, s>>>(map, (int)n_t, n_cols, acc_in, divisor, mean);
     return launch_status("mean_positions_tma_kernel");
   }
   int64_t blocks = (n_cols + kMeanCols - 1) / kMeanCols;
   constexpr int smem = 2 * kMeanRows * kMeanCols * (int)sizeof(float);   // 64 KiB: three CTAs per SM
   PSA_CUDA(cudaFuncSetAttribute(mean_positions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  mean_positions_kernel<<<(unsigned)blocks, kMeanThreads, smem, s>>>(pos, n_t, n_cols, mean);
+  mean_positions_kernel<<<(unsigned)blocks, kMeanThreads, smem, s>>>(pos, n_t, n_cols, acc_in, divisor, mean);
   return launch_status("mean_positions_kernel");
 }
 
@@ -262,9 +273,11 @@ __global__ void __launch_bounds__(256) digitize_kernel(const float* __restrict__
                                                        const float* __restrict__ mean,
                                                        const int32_t* __restrict__ idx, int64_t n_t,
                                                        int64_t n_a, int64_t n_sel, int64_t pitch,
-                                                       int8_t* __restrict__ dig, int32_t* __restrict__ expo) {
-  const int64_t t = blockIdx.x;
-  const float* row = data + t * n_a * 3;
+                                                       int8_t* __restrict__ dig, int32_t* __restrict__ expo,
+                                                       int64_t t0) {
+  // `data` holds the rows [t0, t0 + gridDim.x) of a trajectory of n_t frames; dig / expo describe all n_t frames
+  const int64_t t = t0 + blockIdx.x;
+  const float* row = data + (int64_t)blockIdx.x * n_a * 3;
   __shared__ float s_max[3][8];
   __shared__ int s_exp[3];
 
@@ -345,8 +358,14 @@ __global__ void __launch_bounds__(256) digitize_kernel(const float* __restrict__
 
 int launch_digitize(const float* data, const float* mean, const int32_t* idx, int64_t n_t, int64_t n_a,
                     int64_t n_sel, int64_t pitch, int8_t* dig, int32_t* expo, cudaStream_t s) {
-  if (n_t == 0) return PSA_OK;
-  digitize_kernel<<<(unsigned)n_t, 256, 0, s>>>(data, mean, idx, n_t, n_a, n_sel, pitch, dig, expo);
+  return launch_digitize_rows(data, mean, idx, n_t, n_a, n_sel, pitch, dig, expo, n_t, 0, s);
+}
+
+int launch_digitize_rows(const float* data, const float* mean, const int32_t* idx, int64_t n_rows, int64_t n_a,
+                         int64_t n_sel, int64_t pitch, int8_t* dig, int32_t* expo, int64_t n_t_total, int64_t t0,
+                         cudaStream_t s) {
+  if (n_rows == 0) return PSA_OK;
+  digitize_kernel<<<(unsigned)n_rows, 256, 0, s>>>(data, mean, idx, n_t_total, n_a, n_sel, pitch, dig, expo, t0);
   return launch_status("digitize_kernel");
 }
 

@@ -93,14 +93,75 @@ def gather_k_slices(local: torch.Tensor, n_k_total: int, dst: int = 0, group=Non
     return full
 
 
+def sliced_ingest(calc, proj_groups, local_rows=None, group=None) -> None:
+    """k-independent state from a trajectory whose FRAMES are spread over the ranks.
+
+    Rank r uploads only frames ``shard_range(n_t, r, world)`` - 1/N of the bytes over its own PCIe link -
+    and the ranks then build the shared state together:
+
+    * mean positions: the float32 sum of a column must run in frame order to stay bit-identical with
+      NumPy, so the running sums travel down the ranks (one (n_atoms, 3) message per hop); the last rank
+      divides and broadcasts the mean;
+    * digit planes: every frame row is digitised independently (its own exponent), each rank handles its
+      rows and the row blocks are exchanged with one all-gather (or broadcast) per plane.
+
+    ``local_rows = (positions[t0:t1], velocities[t0:t1])`` when this process holds nothing but its range;
+    otherwise the range is sliced out of ``calc.traj``.  On return every rank's device trajectory has the
+    mean and the digit planes of ``proj_groups`` installed, exactly as after the broadcast ingest.
+    """
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    eng, dtraj = calc.engine, calc.device_trajectory
+    if dtraj.has_state(proj_groups, calc.use_displacements):     # same call sequence on every rank: same answer
+        return
+    n_t, n_a = dtraj.n_t, dtraj.n_a
+    bounds = [shard_range(n_t, r, world) for r in range(world)]
+    t0, t1 = bounds[rank]
+    disp = calc.use_displacements
+    pos_rows = dtraj.upload_rows("pos", t0, t1, None if local_rows is None else local_rows[0])
+    data_rows = pos_rows if disp else dtraj.upload_rows("vel", t0, t1, None if local_rows is None else local_rows[1])
+
+    acc = torch.zeros((n_a, 3), dtype=torch.float32, device=eng.device)
+    if rank > 0:
+        dist.recv(acc, src=rank - 1, group=group)
+    last = rank == world - 1
+    eng.mean_accumulate(pos_rows, acc, n_t if last else 0)
+    if not last:
+        dist.send(acc, dst=rank + 1, group=group)
+    dist.broadcast(acc, src=world - 1, group=group)
+    dtraj.install_mean(acc)
+
+    equal = all(b - a == t1 - t0 for a, b in bounds)
+    for g in proj_groups:
+        idx, idx_dev, n_sel = dtraj.selection(g, disp)
+        pitch = int(eng_pitch(n_sel))
+        dig = eng.empty((3, 4, n_t, pitch), torch.int8)
+        expo = eng.empty((3, n_t), torch.int32)
+        eng.digitize_rows(data_rows, acc if disp else None, idx_dev, n_sel, pitch, dig, expo, n_t, t0)
+        for plane in list(dig.view(12, n_t, pitch).unbind(0)) + list(expo.unbind(0)):
+            if equal:
+                dist.all_gather_into_tensor(plane, plane[t0:t1], group=group)
+            else:
+                for r, (a, b) in enumerate(bounds):
+                    if b > a:
+                        dist.broadcast(plane[a:b], src=r, group=group)
+        dtraj.install_group(idx, disp, dig, expo)
+
+
+def eng_pitch(n_sel: int) -> int:
+    from . import _lib
+    return int(_lib.load().psa_pitch(n_sel))
+
+
 def calculate_sharded(calc, k_points_mags: np.ndarray, k_vectors_3d: np.ndarray, basis_atom_indices=None,
                       basis_atom_types=None, summation_mode: str = "coherent", k_grid_shape=None, src: int = 0,
-                      group=None):
+                      group=None, ingest: str = "broadcast", local_rows=None):
     """``SEDCalculator.calculate`` over all ranks of the process group.
 
-    Every rank calls this with a calculator built on a trajectory of the right *shape*; only ``src``
-    needs real positions/velocities (the others may hold zero-stride placeholders).  Returns the
-    ``SED`` on ``src`` and ``None`` elsewhere.
+    Every rank calls this with a calculator built on a trajectory of the right *shape*.  With
+    ``ingest="broadcast"`` only ``src`` needs real positions/velocities (the others may hold zero-stride
+    placeholders): it uploads and ingests everything and broadcasts the result.  With ``ingest="sliced"``
+    every rank holds (at least) its own range of frames and uploads just that, see :func:`sliced_ingest`.
+    Returns the ``SED`` on ``src`` and ``None`` elsewhere.
     """
     from . import groups as grp
     from .engine import sed_on_device
@@ -117,18 +178,25 @@ def calculate_sharded(calc, k_points_mags: np.ndarray, k_vectors_3d: np.ndarray,
     groups = grp.resolve_sed_groups(traj.types, traj.n_atoms, basis_atom_indices, basis_atom_types, summation_mode)
     complex_out, proj_groups = grp.plan_sed_groups(groups, summation_mode)
 
+    if ingest not in ("broadcast", "sliced"):
+        raise ValueError(f"ingest must be 'broadcast' or 'sliced', got {ingest}")
     with torch.cuda.device(eng.device):
+        if ingest == "sliced":
+            sliced_ingest(calc, proj_groups, local_rows, group)
         # 1. k-independent state: built on src, broadcast once
         tensors: List[Optional[torch.Tensor]] = []
         metas: List[Tuple] = []
-        if rank == src:
+        if ingest == "sliced":
+            got = []
+        elif rank == src:
             tensors.append(dtraj.mean)
             for g in proj_groups:
                 _, _, _, dig, expo = dtraj.group(g, calc.use_displacements)
                 tensors += [dig, expo]
             metas = [(tuple(t.shape), t.dtype) for t in tensors]
-        got = broadcast_tensors(tensors, metas, src, eng.device, group)
-        if rank != src:
+        if ingest == "broadcast":
+            got = broadcast_tensors(tensors, metas, src, eng.device, group)
+        if ingest == "broadcast" and rank != src:
             dtraj.install_mean(got[0])
             for i, g in enumerate(proj_groups):
                 dtraj.install_group(g, calc.use_displacements, got[1 + 2 * i], got[2 + 2 * i])

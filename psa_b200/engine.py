@@ -109,6 +109,20 @@ class Engine:
                   dig.data_ptr(), expo.data_ptr(), self.stream())
         return dig, expo, pitch
 
+    def mean_accumulate(self, rows: torch.Tensor, acc: Optional[torch.Tensor], divide_by: int) -> torch.Tensor:
+        """Running float32 column sums continued over ``rows`` (frames in order); ``/ divide_by`` when > 0."""
+        n_rows, n_a, _ = rows.shape
+        out = acc if acc is not None else self.empty((n_a, 3), torch.float32)
+        self._run("psa_mean_accumulate", 1, rows.data_ptr(), n_rows, n_a, _ptr(acc), divide_by, out.data_ptr(),
+                  self.stream())
+        return out
+
+    def digitize_rows(self, rows: torch.Tensor, mean: Optional[torch.Tensor], idx: Optional[torch.Tensor], n_sel: int,
+                      pitch: int, dig: torch.Tensor, expo: torch.Tensor, n_t_total: int, t0: int) -> None:
+        n_rows, n_a, _ = rows.shape
+        self._run("psa_digitize_rows", 1, rows.data_ptr(), _ptr(mean), _ptr(idx), n_rows, n_a, n_sel, pitch,
+                  dig.data_ptr(), expo.data_ptr(), n_t_total, t0, self.stream())
+
     def phase_digits(self, kvecs: torch.Tensor, mean: torch.Tensor, idx: Optional[torch.Tensor], n_sel: int,
                      pitch: int, rows_alloc: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         n_k = kvecs.shape[0]
@@ -208,6 +222,33 @@ class DeviceTrajectory:
             self.h2d_bytes += src.numel() * 4
         self._dev[which] = dev
         return dev
+
+    def upload_rows(self, which: str, t0: int, t1: int, rows=None) -> torch.Tensor:
+        """Frames [t0, t1) of one array on the device (not cached): the per-rank share of a sliced multi-GPU
+        ingest.  ``rows`` overrides the host source when this process only holds that range."""
+        src = rows if rows is not None else self._host[which][t0:t1]
+        if isinstance(src, torch.Tensor) and src.is_cuda:
+            return src.to(self.engine.device, torch.float32).contiguous()
+        arr = src.numpy() if isinstance(src, torch.Tensor) else np.asarray(src)
+        if arr.dtype != np.float32 or not arr.flags.c_contiguous:
+            arr = np.ascontiguousarray(arr, dtype=np.float32)
+        host = torch.from_numpy(arr)
+        dev = torch.empty(host.shape, dtype=torch.float32, device=self.engine.device)
+        dev.copy_(host, non_blocking=host.is_pinned())
+        self.h2d_bytes += host.numel() * 4
+        return dev
+
+    def has_state(self, groups: Sequence[Optional[np.ndarray]], use_displacements: bool) -> bool:
+        """True when the mean and the digit planes of every group are already on the device."""
+        with self._lock:
+            return self._mean is not None and all(self._group_key(g, use_displacements)[0] in self._groups for g in groups)
+
+    def selection(self, idx: Optional[np.ndarray], use_displacements: bool):
+        """``(key-normalised idx, idx_dev|None, n_sel)`` of an atom selection."""
+        key, idx = self._group_key(idx, use_displacements)
+        if idx is None:
+            return idx, None, self.n_a
+        return idx, self._index_tensor(key, idx), int(idx.size)
 
     @property
     def positions(self) -> torch.Tensor:

@@ -49,6 +49,30 @@ def test_mean_positions_unaligned_base_uses_fallback(eng):
     np.testing.assert_array_equal(got, np.mean(pos.cpu().numpy(), axis=0, dtype=np.float32))
 
 
+def test_ingest_by_frame_ranges_is_bit_identical(eng):
+    """The multi-GPU sliced ingest: running sums continued over frame ranges and row-range digitising give
+    the bits of the one-shot kernels."""
+    rng = np.random.default_rng(11)
+    n_t, n_a = 1000, 48
+    pos = (rng.random((n_t, n_a, 3)) * 20 + rng.standard_normal((n_t, n_a, 3)) * 0.05).astype(np.float32)
+    d = dev(eng, pos)
+    want = eng.mean_positions(d)
+    acc = None
+    cuts = [0, 333, 334, 900, 1000]
+    for i, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+        acc = eng.mean_accumulate(d[a:b].contiguous(), acc, n_t if i == len(cuts) - 2 else 0)
+    assert torch.equal(acc, want)
+    np.testing.assert_array_equal(acc.cpu().numpy(), np.mean(pos, axis=0, dtype=np.float32))
+    idx = dev(eng, np.array([1, 5, 6, 7, 40, 41], np.int32))
+    for mean, sel, n_sel in ((None, None, n_a), (want, idx, 6)):
+        dig, expo, pitch = eng.digitize(d, mean, sel, n_sel)
+        dig2, expo2 = torch.zeros_like(dig), torch.zeros_like(expo)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            eng.digitize_rows(d[a:b].contiguous(), mean, sel, n_sel, pitch, dig2, expo2, n_t, a)
+        assert torch.equal(expo2, expo)
+        assert torch.equal(dig2[..., :n_sel], dig[..., :n_sel])
+
+
 @pytest.mark.parametrize("case", ["all", "subset", "displacement", "zeros"])
 def test_digitize_exact(eng, case):
     rng = np.random.default_rng(5)
@@ -520,7 +544,10 @@ def test_k_sharded_two_gpus_equals_single_gpu():
                           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "MULTIGPU_CHECK world=2 results=[True, True, True]" in out.stdout
+    import re as _re
+    m = _re.search(r"MULTIGPU_CHECK world=2 results=\[([^\]]*)\]", out.stdout)
+    # 3 broadcast-ingest cases + 8 sliced-ingest cases (even / ragged frame split x velocity / displacement x 2 modes)
+    assert m and m.group(1).split(", ") == ["True"] * 11, out.stdout[-2000:]
 
 
 def test_npy_cache_streams_to_device(gold_si, tmp_path):
