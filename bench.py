@@ -326,7 +326,7 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms.item()) / args.steps
-    launches = (eng.launches - launches0) // args.steps
+    launches = eng.launches - launches0                         # this rank's kernels inside the timed region
 
     units_local = units_of(cfg, traj.types, traj.n_frames, list(zip(jobs, slices)))
     units_t = torch.tensor([float(units_local)], dtype=torch.float64, device=dev)
@@ -477,7 +477,7 @@ def main():
                        "l2_policy": "inputs larger than L2 (trajectory %.0f MB per array)" % (traj.positions.nbytes / 1e6),
                        "step": "mean positions + digit planes + phase table + tcgen05 projection + FFT/assembly"},
             "roofline": roof, "rooflines": rooflines, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "ised": ised,
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "gpu_launches_per_step": int(launches) // max(1, args.steps), "clocks": clocks,
         }
         emit(line)
     if world > 1:

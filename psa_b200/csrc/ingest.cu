@@ -269,7 +269,7 @@ __device__ __forceinline__ void load_quad(const float* __restrict__ row, const f
   }
 }
 
-__global__ void __launch_bounds__(256) digitize_kernel(const float* __restrict__ data,
+__global__ void __launch_bounds__(512) digitize_kernel(const float* __restrict__ data,
                                                        const float* __restrict__ mean,
                                                        const int32_t* __restrict__ idx, int64_t n_t,
                                                        int64_t n_a, int64_t n_sel, int64_t pitch,
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256) digitize_kernel(const float* __restrict__
   // `data` holds the rows [t0, t0 + gridDim.x) of a trajectory of n_t frames; dig / expo describe all n_t frames
   const int64_t t = t0 + blockIdx.x;
   const float* row = data + (int64_t)blockIdx.x * n_a * 3;
-  __shared__ float s_max[3][8];
+  __shared__ float s_max[3][32];
   __shared__ int s_exp[3];
 
   float mx[3] = {0.f, 0.f, 0.f};
@@ -365,7 +365,8 @@ int launch_digitize_rows(const float* data, const float* mean, const int32_t* id
                          int64_t n_sel, int64_t pitch, int8_t* dig, int32_t* expo, int64_t n_t_total, int64_t t0,
                          cudaStream_t s) {
   if (n_rows == 0) return PSA_OK;
-  digitize_kernel<<<(unsigned)n_rows, 256, 0, s>>>(data, mean, idx, n_t_total, n_a, n_sel, pitch, dig, expo, t0);
+  // 512 threads for contiguous rows, 256 for gathered ones (bench.py on C1 / C2: 0.131 vs 0.142 ms, 0.242 vs 0.252 ms)
+  digitize_kernel<<<(unsigned)n_rows, idx == nullptr ? 512 : 256, 0, s>>>(data, mean, idx, n_t_total, n_a, n_sel, pitch, dig, expo, t0);
   return launch_status("digitize_kernel");
 }
 
