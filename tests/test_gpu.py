@@ -73,22 +73,25 @@ def test_ingest_by_frame_ranges_is_bit_identical(eng):
         assert torch.equal(dig2[..., :n_sel], dig[..., :n_sel])
 
 
-@pytest.mark.parametrize("case", ["all", "subset", "displacement", "zeros"])
+# "staged": a gathered selection whose frame row is 16-byte aligned goes through the bulk-copy (shared memory) path
+@pytest.mark.parametrize("case", ["all", "subset", "displacement", "zeros", "staged", "staged_displacement"])
 def test_digitize_exact(eng, case):
     rng = np.random.default_rng(5)
-    n_t, n_a = 33, 203
+    n_t, n_a = 33, (204 if case.startswith("staged") else 203)
     data = (rng.standard_normal((n_t, n_a, 3)) * np.array([3.0, 0.02, 700.0])).astype(np.float32)
     idx, mean = None, None
     if case == "subset":
         idx = np.array([5, 0, 77, 77, 202, 13, 14, 15, 100], np.int32)
-    if case == "displacement":
+    if case.startswith("staged"):
+        idx = np.concatenate([np.arange(0, 204, 2), [203, 1, 1]]).astype(np.int32)
+    if case in ("displacement", "staged_displacement"):
         mean = (rng.random((n_a, 3)) * 3).astype(np.float32)
     if case == "zeros":
         data[:, :, 1] = 0.0
         data[7] = 0.0
     sel = data if idx is None else data[:, idx, :]
     if mean is not None:
-        sel = sel - mean[None]
+        sel = sel - (mean if idx is None else mean[idx])[None]
     n_sel = sel.shape[1]
     dig, expo, pitch = eng.digitize(dev(eng, data), None if mean is None else dev(eng, mean),
                                     None if idx is None else dev(eng, idx), n_sel)
