@@ -138,8 +138,11 @@ struct TileCoord {
 // much as a full one because the M-side operand read does not shrink with N.
 __device__ __forceinline__ TileCoord decode_tile(int tile, int r_tiles, int t_tiles, int rows) {
   TileCoord c;
-  c.r_tile = tile % r_tiles;          // row tiles fastest: concurrent CTAs share the same trajectory strip
+  // Row tiles fastest (concurrent CTAs share the same trajectory strip), rotated by the strip index: the last
+  // row tile is the narrow one, and with a fixed order a CTA whose stride is even in r_tiles would only ever
+  // see wide tiles (C2: 74 CTA pairs, 4 row tiles - half the pairs did 11 wide tiles, the others mixed).
   int n = tile / r_tiles;
+  c.r_tile = (tile + n) % r_tiles;
   c.pol = n / t_tiles;
   c.t_tile = n % t_tiles;
   const int per_tile = (((rows + r_tiles - 1) / r_tiles) + 15) & ~15;
