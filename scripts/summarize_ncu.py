@@ -69,9 +69,15 @@ def full(src, dst, workload=None):
     Path(dst).write_text("\n".join(out) + "\n")
     print("\n".join(out))
     if workload:
-        api = {"mean_positions_kernel": "psa_mean_positions", "mean_positions_tma_kernel": "psa_mean_positions", "digitize_kernel": "psa_digitize",
-               "phase_digits_kernel": "psa_phase_digits", "tc::project_tc_kernel": "psa_project",
-               "fft_sed_kernel<0>": "psa_fft_sed", "fft_sed_kernel<1>": "psa_fft_sed"}
+        import re
+
+        def api_name(kernel):                       # kernel symbol -> the C-ABI call that bench.py times
+            base = re.sub(r"<.*>$", "", kernel).split("::")[-1]
+            return {"mean_positions_kernel": "psa_mean_positions", "mean_positions_tma_kernel": "psa_mean_positions",
+                    "digitize_kernel": "psa_digitize", "phase_digits_kernel": "psa_phase_digits",
+                    "project_tc_kernel": "psa_project", "project_tc2_kernel": "psa_project",
+                    "fft_sed_kernel": "psa_fft_sed"}.get(base, kernel)
+        api = {k: api_name(k) for k in traffic}
         p = Path(dst).parent / "ncu_traffic.json"
         data = json.loads(p.read_text()) if p.exists() else {}
         data.setdefault(workload, {}).update({api.get(k, k): v for k, v in traffic.items()})
