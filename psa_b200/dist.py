@@ -120,31 +120,49 @@ def sliced_ingest(calc, proj_groups, local_rows=None, group=None) -> None:
     pos_rows = dtraj.upload_rows("pos", t0, t1, None if local_rows is None else local_rows[0])
     data_rows = pos_rows if disp else dtraj.upload_rows("vel", t0, t1, None if local_rows is None else local_rows[1])
 
-    acc = torch.zeros((n_a, 3), dtype=torch.float32, device=eng.device)
-    if rank > 0:
-        dist.recv(acc, src=rank - 1, group=group)
-    last = rank == world - 1
-    eng.mean_accumulate(pos_rows, acc, n_t if last else 0)
-    if not last:
-        dist.send(acc, dst=rank + 1, group=group)
-    dist.broadcast(acc, src=world - 1, group=group)
+    acc = chain_running_sum(torch.zeros((n_a, 3), dtype=torch.float32, device=eng.device),
+                            lambda a, last: eng.mean_accumulate(pos_rows, a, n_t if last else 0), group)
     dtraj.install_mean(acc)
 
-    equal = all(b - a == t1 - t0 for a, b in bounds)
     for g in proj_groups:
         idx, idx_dev, n_sel = dtraj.selection(g, disp)
         pitch = int(eng_pitch(n_sel))
         dig = eng.empty((3, 4, n_t, pitch), torch.int8)
         expo = eng.empty((3, n_t), torch.int32)
         eng.digitize_rows(data_rows, acc if disp else None, idx_dev, n_sel, pitch, dig, expo, n_t, t0)
-        for plane in list(dig.view(12, n_t, pitch).unbind(0)) + list(expo.unbind(0)):
-            if equal:
-                dist.all_gather_into_tensor(plane, plane[t0:t1], group=group)
-            else:
-                for r, (a, b) in enumerate(bounds):
-                    if b > a:
-                        dist.broadcast(plane[a:b], src=r, group=group)
+        exchange_row_blocks(list(dig.view(12, n_t, pitch).unbind(0)) + list(expo.unbind(0)), bounds, group)
         dtraj.install_group(idx, disp, dig, expo)
+
+
+def chain_running_sum(acc: torch.Tensor, accumulate, group=None) -> torch.Tensor:
+    """Ordered reduction over the ranks: rank 0 starts from ``acc``, every rank continues the running value
+    with ``accumulate(acc, is_last_rank)`` (in place) and hands it to the next one; the last rank's result
+    is broadcast to all.  The order of operations is that of a single process walking the ranks' data in
+    rank order - which is what keeps a float32 sum bit-identical."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if rank > 0:
+        dist.recv(acc, src=rank - 1, group=group)
+    accumulate(acc, rank == world - 1)
+    if rank < world - 1:
+        dist.send(acc, dst=rank + 1, group=group)
+    dist.broadcast(acc, src=world - 1, group=group)
+    return acc
+
+
+def exchange_row_blocks(planes, bounds, group=None) -> None:
+    """Every tensor in ``planes`` has its leading axis split over the ranks as ``bounds[r] = (a, b)``; each
+    rank has filled its own block.  Afterwards every rank holds every block (in place): one all-gather
+    per plane when the blocks have equal length, one broadcast per (plane, rank) otherwise."""
+    rank = dist.get_rank(group)
+    t0, t1 = bounds[rank]
+    equal = all(b - a == t1 - t0 for a, b in bounds)
+    for plane in planes:
+        if equal:
+            dist.all_gather_into_tensor(plane, plane[t0:t1], group=group)
+        else:
+            for r, (a, b) in enumerate(bounds):
+                if b > a:
+                    dist.broadcast(plane[a:b], src=r, group=group)
 
 
 def eng_pitch(n_sel: int) -> int:

@@ -70,3 +70,57 @@ def test_gather_and_broadcast_over_gloo(world, n_k):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(all(r) for r in results), results
+
+
+# ------------------------------------------------------------------ sliced ingest: chain + block exchange (host logic)
+def _seq_sum_f32(acc: np.ndarray, rows: np.ndarray) -> np.ndarray:
+    """acc (+) rows[0] (+) rows[1] ... in float32, in order - the stand-in for psa_mean_accumulate."""
+    if rows.shape[0] == 0:
+        return acc
+    return np.cumsum(np.concatenate([acc[None], rows], axis=0), axis=0, dtype=np.float32)[-1]
+
+
+def _sliced_worker(rank, world, port, n_t, result_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(7)
+        pos = (rng.random((n_t, 5, 3)) * 30 + rng.standard_normal((n_t, 5, 3)) * 0.01).astype(np.float32)
+        bounds = [pdist.shard_range(n_t, r, world) for r in range(world)]
+        t0, t1 = bounds[rank]
+
+        def accumulate(acc, last):
+            out = _seq_sum_f32(acc.numpy().copy(), pos[t0:t1])
+            if last:
+                out = out / np.float32(n_t)
+            acc.copy_(torch.from_numpy(out))
+
+        mean = pdist.chain_running_sum(torch.zeros((5, 3), dtype=torch.float32), accumulate)
+        ok_mean = bool(np.array_equal(mean.numpy(), np.mean(pos, axis=0, dtype=np.float32)))
+        # row blocks: every rank fills its own rows of two "planes", afterwards all ranks hold everything
+        want = [torch.arange(n_t * 4, dtype=torch.int32).reshape(n_t, 4), torch.arange(n_t, dtype=torch.int32) * 3]
+        planes = [torch.full_like(w, -1) for w in want]
+        for p, w in zip(planes, want):
+            p[t0:t1] = w[t0:t1]
+        pdist.exchange_row_blocks(planes, bounds)
+        ok_planes = all(bool(torch.equal(p, w)) for p, w in zip(planes, want))
+        result_q.put((ok_mean, ok_planes))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_t", [(2, 64), (2, 7), (3, 100), (3, 2)])
+def test_sliced_ingest_chain_and_exchange_over_gloo(world, n_t):
+    """The ordered float32 running sum handed from rank to rank equals np.mean(dtype=float32) bit for bit, and
+    the row-block exchange (all-gather for equal blocks, broadcasts for ragged or empty ones) fills every rank."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sliced_worker, args=(r, world, port, n_t, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(all(r) for r in results), results
