@@ -276,6 +276,36 @@ __device__ __forceinline__ void load_quad(const float* __restrict__ row, const f
   }
 }
 
+// exponent e with m < 2^e (kExpMin for an all-zero or non-finite row)
+__device__ __forceinline__ int row_exponent(float m) {
+  int e = kExpMin;
+  if (m > 0.f && isfinite(m)) {
+    frexpf(m, &e);                         // m = f * 2^e with f in [0.5,1)  =>  m < 2^e
+    e = max(kExpMin, min(kExpMax, e));
+  }
+  return e;
+}
+
+// Digit-plane words of four atoms.  Digits without a carry chain: with Y = X + 0x00808080 the low three bytes
+// of Y are d_i + 128 and the top byte is d3, so the bytes of Z = Y ^ 0x00808080 ARE the balanced digits
+// (identical to balanced_digits(); |X| <= 2^30 leaves room for the bias).  The four atoms are then turned
+// into four plane words by a 4 x 4 byte transpose (eight PRMTs).
+__device__ __forceinline__ void quad_words(const float (&v)[12], const float (&scale)[3], uint32_t (&word)[3][kSlices]) {
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    uint32_t z[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      z[q] = ((uint32_t)__float2int_rn(v[q * 3 + p] * scale[p]) + 0x00808080u) ^ 0x00808080u;
+    const uint32_t lo01 = __byte_perm(z[0], z[1], 0x5140), hi01 = __byte_perm(z[0], z[1], 0x7362);
+    const uint32_t lo23 = __byte_perm(z[2], z[3], 0x5140), hi23 = __byte_perm(z[2], z[3], 0x7362);
+    word[p][0] = __byte_perm(lo01, lo23, 0x5410);
+    word[p][1] = __byte_perm(lo01, lo23, 0x7632);
+    word[p][2] = __byte_perm(hi01, hi23, 0x5410);
+    word[p][3] = __byte_perm(hi01, hi23, 0x7632);
+  }
+}
+
 // kStaged (gathered selections whose frame row fits shared memory): the row is fetched once with one bulk
 // copy (cp.async.bulk + mbarrier) and both passes gather from shared memory; scalar gathers from global memory
 // kept the LSU/L1 busier than HBM (ncu: 172 M sector requests, issue slots 57 %, DRAM 61 %).
@@ -338,11 +368,7 @@ __global__ void __launch_bounds__(512) digitize_kernel(const float* __restrict__
   if (threadIdx.x < 3) {
     float m = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s_max[threadIdx.x][w]);
-    int e = kExpMin;
-    if (m > 0.f && isfinite(m)) {
-      frexpf(m, &e);                       // m = f * 2^e with f in [0.5,1)  =>  m < 2^e
-      e = max(kExpMin, min(kExpMax, e));
-    }
+    const int e = row_exponent(m);
     s_exp[threadIdx.x] = e;
     expo[threadIdx.x * n_t + t] = e;
   }
@@ -353,28 +379,12 @@ __global__ void __launch_bounds__(512) digitize_kernel(const float* __restrict__
   for (int p = 0; p < 3; ++p) scale[p] = exp2f((float)(kFracBits - s_exp[p]));   // exact power of two
 
   const int64_t plane = n_t * pitch;                 // bytes of one (pol, slice) plane
-  // Digits without a carry chain: with Y = X + 0x00808080 the low three bytes of Y are d_i + 128 and the
-  // top byte is d3, so the bytes of Z = Y ^ 0x00808080 ARE the balanced digits (identical to
-  // balanced_digits(); |X| <= 2^30 leaves room for the bias).  Four atoms are then turned into four plane
-  // words by a 4 x 4 byte transpose (eight PRMTs).
   for (int64_t j0 = (int64_t)threadIdx.x * 4; j0 < pitch; j0 += (int64_t)blockDim.x * 4) {
     uint32_t word[3][kSlices] = {};
     if (j0 < n_sel) {
       float v[12];
       load_quad<kStaged>(row, mean, idx, j0, n_sel, v);      // entries past n_sel come back as zeros -> zero digits
-#pragma unroll
-      for (int p = 0; p < 3; ++p) {
-        uint32_t z[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          z[q] = ((uint32_t)__float2int_rn(v[q * 3 + p] * scale[p]) + 0x00808080u) ^ 0x00808080u;
-        const uint32_t lo01 = __byte_perm(z[0], z[1], 0x5140), hi01 = __byte_perm(z[0], z[1], 0x7362);
-        const uint32_t lo23 = __byte_perm(z[2], z[3], 0x5140), hi23 = __byte_perm(z[2], z[3], 0x7362);
-        word[p][0] = __byte_perm(lo01, lo23, 0x5410);
-        word[p][1] = __byte_perm(lo01, lo23, 0x7632);
-        word[p][2] = __byte_perm(hi01, hi23, 0x5410);
-        word[p][3] = __byte_perm(hi01, hi23, 0x7632);
-      }
+      quad_words(v, scale, word);
     }
 #pragma unroll
     for (int p = 0; p < 3; ++p)
@@ -382,6 +392,94 @@ __global__ void __launch_bounds__(512) digitize_kernel(const float* __restrict__
       for (int sl = 0; sl < kSlices; ++sl)
         *reinterpret_cast<uint32_t*>(dig + (int64_t)(p * kSlices + sl) * plane + t * pitch + j0) = word[p][sl];
   }
+}
+
+// Long rows (more atoms than one CTA's shared memory holds, e.g. 64 000 atoms = 768 KB per frame): the two-pass
+// kernel above re-reads the row from HBM for the digit pass (ncu on C5: 75 GB of traffic for 50 GB of work).
+// Here a cluster of kDigCluster CTAs owns one frame: each CTA fetches its 1/8 of the row with one bulk copy
+// and keeps it in shared memory, the per-polarisation maxima are exchanged through distributed shared memory,
+// and the digits are produced from the staged copy - the frame is read from HBM exactly once.
+constexpr int kDigCluster = 8;
+__global__ void __cluster_dims__(kDigCluster, 1, 1) __launch_bounds__(256)
+digitize_cluster_kernel(const float* __restrict__ data, const float* __restrict__ mean, int64_t n_t, int64_t n_a,
+                        int64_t pitch, int slice_atoms, int8_t* __restrict__ dig, int32_t* __restrict__ expo,
+                        int64_t t0) {
+  extern __shared__ __align__(128) float s_row[];     // this CTA's slice of the frame
+  __shared__ uint64_t row_bar;
+  __shared__ float s_max[3][8], s_loc[3];
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int64_t frame = blockIdx.x / kDigCluster, t = t0 + frame;
+  const int64_t a0 = (int64_t)rank * slice_atoms;
+  const int n_loc = (int)max((int64_t)0, min(n_a, a0 + slice_atoms) - a0);     // multiple of 4, > 0
+  const uint32_t bytes = (uint32_t)n_loc * 3 * sizeof(float);
+  if (threadIdx.x == 0) {
+    mbar_init(&row_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&row_bar, bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(s_row)),
+                 "l"(data + (frame * n_a + a0) * 3), "r"(bytes), "r"(smem_addr(&row_bar))
+                 : "memory");
+  }
+  __syncthreads();
+  mbar_wait(&row_bar, 0);
+  const float* lmean = mean != nullptr ? mean + a0 * 3 : nullptr;
+
+  float mx[3] = {0.f, 0.f, 0.f};
+  for (int j0 = threadIdx.x * 4; j0 < n_loc; j0 += blockDim.x * 4) {
+    float v[12];
+    load_quad<true>(s_row, lmean, nullptr, j0, n_loc, v);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) mx[i % 3] = fmaxf(mx[i % 3], fabsf(v[i]));
+  }
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    float m = mx[p];
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_max[p][threadIdx.x >> 5] = m;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float m = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s_max[threadIdx.x][w]);
+    s_loc[threadIdx.x] = m;
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  float scale[3];
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {                        // every thread folds the eight CTAs' maxima (24 remote reads)
+    float m = 0.f;
+    for (uint32_t c = 0; c < kDigCluster; ++c) {
+      uint32_t remote;
+      float val;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_addr(&s_loc[p])), "r"(c));
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(val) : "r"(remote) : "memory");
+      m = fmaxf(m, val);
+    }
+    const int e = row_exponent(m);
+    if (rank == 0 && threadIdx.x == 0) expo[p * n_t + t] = e;
+    scale[p] = exp2f((float)(kFracBits - e));
+  }
+
+  const int64_t plane = n_t * pitch;
+  // this CTA's atoms, plus - on the last CTA - the zero padding up to the pitch
+  const int64_t j_end = rank == kDigCluster - 1 ? pitch - a0 : n_loc;
+  for (int64_t j0 = (int64_t)threadIdx.x * 4; j0 < j_end; j0 += (int64_t)blockDim.x * 4) {
+    uint32_t word[3][kSlices] = {};
+    if (j0 < n_loc) {
+      float v[12];
+      load_quad<true>(s_row, lmean, nullptr, j0, n_loc, v);
+      quad_words(v, scale, word);
+    }
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int sl = 0; sl < kSlices; ++sl)
+        *reinterpret_cast<uint32_t*>(dig + (int64_t)(p * kSlices + sl) * plane + t * pitch + a0 + j0) = word[p][sl];
+  }
+  // nobody leaves while a peer may still read its maxima
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 int launch_digitize(const float* data, const float* mean, const int32_t* idx, int64_t n_t, int64_t n_a,
@@ -401,6 +499,16 @@ int launch_digitize_rows(const float* data, const float* mean, const int32_t* id
     digitize_kernel<true><<<(unsigned)n_rows, 256, row_bytes, s>>>(data, mean, idx, n_t_total, n_a, n_sel, pitch, dig,
                                                                      expo, t0);
     return launch_status("digitize_kernel<staged>");
+  }
+  if (idx == nullptr && !no_stage && row_bytes > 200 * 1024 && n_a % 4 == 0 && (reinterpret_cast<uintptr_t>(data) & 15) == 0) {
+    const int slice_atoms = (int)(((n_a + kDigCluster - 1) / kDigCluster + 3) / 4 * 4);
+    const size_t slice_bytes = (size_t)slice_atoms * 3 * sizeof(float);
+    if (slice_bytes <= 100 * 1024 && (int64_t)slice_atoms * (kDigCluster - 1) < n_a) {   // two clusters per SM pair
+      PSA_CUDA(cudaFuncSetAttribute(digitize_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice_bytes));
+      digitize_cluster_kernel<<<(unsigned)(n_rows * kDigCluster), 256, slice_bytes, s>>>(data, mean, n_t_total, n_a, pitch,
+                                                                                          slice_atoms, dig, expo, t0);
+      return launch_status("digitize_cluster_kernel");
+    }
   }
   // 512 threads for contiguous rows, 256 for gathered ones (bench.py on C1 / C2: 0.131 vs 0.142 ms, 0.242 vs 0.252 ms)
   digitize_kernel<false><<<(unsigned)n_rows, idx == nullptr ? 512 : 256, 0, s>>>(data, mean, idx, n_t_total, n_a, n_sel,

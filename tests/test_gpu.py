@@ -104,6 +104,26 @@ def test_digitize_exact(eng, case):
         np.testing.assert_array_equal(d[pol, :, :, :n_sel], M.balanced_digits(x_ref[pol]))
 
 
+@pytest.mark.parametrize("n_a,with_mean", [(17072, False), (17076, True), (40000, False)])
+def test_digitize_long_rows_cluster_path(eng, n_a, with_mean):
+    """Rows longer than 200 KB: a cluster of eight CTAs stages one frame in shared memory (single HBM read),
+    maxima exchanged through distributed shared memory.  Same digits as the integer model."""
+    rng = np.random.default_rng(n_a)
+    n_t = 5
+    data = (rng.standard_normal((n_t, n_a, 3)) * np.array([3.0, 0.02, 700.0])).astype(np.float32)
+    data[2, n_a - 1, 2] = 5000.0                      # the row maximum sits in the last CTA's slice
+    data[3, 0, 0] = -77.0                             # ... and in the first one's
+    mean = (rng.random((n_a, 3)) * 3).astype(np.float32) if with_mean else None
+    sel = data if mean is None else data - mean[None]
+    dig, expo, pitch = eng.digitize(dev(eng, data), None if mean is None else dev(eng, mean), None, n_a)
+    x_ref, e_ref = M.digitize(sel)
+    np.testing.assert_array_equal(expo.cpu().numpy(), e_ref)
+    d = dig.cpu().numpy()
+    assert not d[:, :, :, n_a:].any()
+    for pol in range(3):
+        np.testing.assert_array_equal(d[pol, :, :, :n_a], M.balanced_digits(x_ref[pol]))
+
+
 def test_phase_digits(eng):
     rng = np.random.default_rng(6)
     n_a, n_k = 500, 23
