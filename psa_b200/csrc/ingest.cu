@@ -396,19 +396,19 @@ __global__ void __launch_bounds__(512) digitize_kernel(const float* __restrict__
 
 // Long rows (more atoms than one CTA's shared memory holds, e.g. 64 000 atoms = 768 KB per frame): the two-pass
 // kernel above re-reads the row from HBM for the digit pass (ncu on C5: 75 GB of traffic for 50 GB of work).
-// Here a cluster of kDigCluster CTAs owns one frame: each CTA fetches its 1/8 of the row with one bulk copy
+// Here a cluster of 8 CTAs owns one frame: each CTA fetches its share of the row with one bulk copy
 // and keeps it in shared memory, the per-polarisation maxima are exchanged through distributed shared memory,
 // and the digits are produced from the staged copy - the frame is read from HBM exactly once.
-constexpr int kDigCluster = 8;
-__global__ void __cluster_dims__(kDigCluster, 1, 1) __launch_bounds__(256)
+__global__ void __launch_bounds__(256)
 digitize_cluster_kernel(const float* __restrict__ data, const float* __restrict__ mean, int64_t n_t, int64_t n_a,
                         int64_t pitch, int slice_atoms, int8_t* __restrict__ dig, int32_t* __restrict__ expo,
                         int64_t t0) {
   extern __shared__ __align__(128) float s_row[];     // this CTA's slice of the frame
   __shared__ uint64_t row_bar;
   __shared__ float s_max[3][8], s_loc[3];
-  uint32_t rank;
+  uint32_t rank, kDigCluster;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(kDigCluster));
   const int64_t frame = blockIdx.x / kDigCluster, t = t0 + frame;
   const int64_t a0 = (int64_t)rank * slice_atoms;
   const int n_loc = (int)max((int64_t)0, min(n_a, a0 + slice_atoms) - a0);     // multiple of 4, > 0
@@ -448,7 +448,7 @@ digitize_cluster_kernel(const float* __restrict__ data, const float* __restrict_
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   float scale[3];
 #pragma unroll
-  for (int p = 0; p < 3; ++p) {                        // every thread folds the eight CTAs' maxima (24 remote reads)
+  for (int p = 0; p < 3; ++p) {                        // every thread folds the CTAs' maxima (3 x cluster size remote reads)
     float m = 0.f;
     for (uint32_t c = 0; c < kDigCluster; ++c) {
       uint32_t remote;
@@ -501,12 +501,29 @@ int launch_digitize_rows(const float* data, const float* mean, const int32_t* id
     return launch_status("digitize_kernel<staged>");
   }
   if (idx == nullptr && !no_stage && row_bytes > 200 * 1024 && n_a % 4 == 0 && (reinterpret_cast<uintptr_t>(data) & 15) == 0) {
-    const int slice_atoms = (int)(((n_a + kDigCluster - 1) / kDigCluster + 3) / 4 * 4);
-    const size_t slice_bytes = (size_t)slice_atoms * 3 * sizeof(float);
-    if (slice_bytes <= 100 * 1024 && (int64_t)slice_atoms * (kDigCluster - 1) < n_a) {   // two clusters per SM pair
+    // 8 CTAs with <= 100 KB slices (two clusters' CTAs per SM).  16-CTA clusters with 48 KB slices were measured
+    // slower (scripts/digitize_tune.py, 64 000 atoms: 4.0 vs 4.7 TB/s); PSA_DIG_CLUSTER=16 selects them for A/B runs.
+    static const int forced = getenv("PSA_DIG_CLUSTER") ? atoi(getenv("PSA_DIG_CLUSTER")) : 8;
+    for (int C : {16, 8}) {
+      if (C != forced) continue;
+      const int slice_atoms = (int)(((n_a + C - 1) / C + 3) / 4 * 4);
+      const size_t slice_bytes = (size_t)slice_atoms * 3 * sizeof(float);
+      if (slice_bytes > (C == 16 ? 52u : 100u) * 1024 || (int64_t)slice_atoms * (C - 1) >= n_a) continue;
       PSA_CUDA(cudaFuncSetAttribute(digitize_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice_bytes));
-      digitize_cluster_kernel<<<(unsigned)(n_rows * kDigCluster), 256, slice_bytes, s>>>(data, mean, n_t_total, n_a, pitch,
-                                                                                          slice_atoms, dig, expo, t0);
+      PSA_CUDA(cudaFuncSetAttribute(digitize_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(n_rows * C));
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = slice_bytes;
+      cfg.stream = s;
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = (unsigned)C;
+      attr.val.clusterDim.y = 1;
+      attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      PSA_CUDA(cudaLaunchKernelEx(&cfg, digitize_cluster_kernel, data, mean, n_t_total, n_a, pitch, slice_atoms, dig, expo, t0));
       return launch_status("digitize_cluster_kernel");
     }
   }
