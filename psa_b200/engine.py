@@ -9,6 +9,11 @@ Pipeline for one ``calculate`` (reference: src/psa/core/sed_calculator.py:182-33
 
     upload trajectory ─► mean positions ─► digit planes of the projected series   (once per group)
     for each k-chunk:  phase digit planes ─► tensor-core projection ─► FFT + assembly into the result
+
+A k-set longer than one chunk can be streamed: each chunk's spectra leave for pinned host memory on a side
+stream while the next chunk is projected (``sed_on_device(host_out=...)``).  On several GPUs the ingest can
+be sliced by frames (``DeviceTrajectory.upload_rows`` + ``Engine.mean_accumulate`` / ``digitize_rows``, driven
+by ``psa_b200.dist.sliced_ingest``).
 """
 from __future__ import annotations
 

@@ -219,3 +219,15 @@ def test_npy_cache_roundtrip_matches_reference_loader(tmp_path, gold_si):
         assert ref.dt_ps == back.dt_ps
     with pytest.raises(ValueError):
         cache.load_npy_cache(fake, dt=0.0)
+
+
+def test_mode_validation_needs_no_gpu():
+    """Argument errors surface before any device work (reference: sed_calculator.py:190-191)."""
+    from psa_b200 import SEDCalculator, synth
+    spec = synth.si_spec("tiny", n_cells=1, n_frames=8, seed=1)
+    calc = SEDCalculator(spec.trajectory(threads=1), *spec.cells)
+    mags, vecs = calc.get_k_path([1, 0, 0], 1.0, 3)
+    for call in (calc.calculate, calc.calculate_intensity):
+        with pytest.raises(ValueError, match="summation_mode"):
+            call(mags, vecs, summation_mode="partially coherent")
+    assert calc._engine is None                      # nothing touched the GPU
