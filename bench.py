@@ -33,7 +33,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "k-points*timesteps*atoms/sec"
+METRIC = "k-points\u00b7timesteps\u00b7atoms/sec"      # BASELINE.json's metric, verbatim
 UNIT = "k*t*atom/s"
 FLOP_PER_UNIT = 12.0          # 3 pol x (2 mul + 2 add): real series x complex phase
 
