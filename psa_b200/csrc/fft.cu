@@ -19,8 +19,9 @@
 // kernel is latency-bound at 24 warps per SM (80 registers per thread for float64 butterflies).
 // Tried and measured slower or equal in round 1 (scripts/fft_tune.py), and therefore not kept:
 //   * float32 storage with float64 butterflies (same speed, 2x the rounding error);
-//   * clusters of 2-8 ADJACENT columns exchanging spectra through distributed shared memory so that
-//     the frequency-major result is written in 32-64 byte runs (0.80-0.86 ms vs 0.76 ms);
+//   * clusters of 2-8 ADJACENT columns exchanging spectra through distributed shared memory with an extra
+//     pull-and-transpose pass in shared memory (0.80-0.86 ms vs 0.76 ms); the lean variant that reads the
+//     peers' staged spectra directly while storing (fft_sed_cluster_kernel) does pay, 4 %, and is the default;
 //   * the R CTAs of ONE column as a cluster, each loading 1/R of the samples and gathering the rest
 //     from its peers' shared memory instead of re-reading them from L2 (0.90 ms vs 0.78 ms);
 //   * twiddles factored into two 64-entry shared-memory tables instead of L2-resident per-pass tables
@@ -92,6 +93,28 @@ __device__ __forceinline__ cd cadd(cd a, cd b) { return mk(a.x + b.x, a.y + b.y)
 __device__ __forceinline__ cd csub(cd a, cd b) { return mk(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ cd mul_neg_i(cd a) { return mk(a.y, -a.x); }   // a * (-i)
 __device__ __forceinline__ int phys(int p) { return p + (p >> 4); }
+
+// thread-block cluster helpers
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_size() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float2 ld_peer(uint32_t smem_addr, uint32_t rank) {
+  uint32_t remote;
+  float2 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_addr), "r"(rank));
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(remote) : "memory");
+  return v;
+}
 
 // forward DFTs in natural output order (no external twiddles)
 __device__ __forceinline__ void bfly2(cd& a0, cd& a1) {
@@ -658,6 +681,73 @@ __global__ void __launch_bounds__(kFftThreads, kFftMinCtas) fft_sed_kernel(SedAr
   }
 }
 
+// Coherent result with wider stores (default C = 4; PSA_FFT_CLUSTER=1|2|4): the CTAs of C adjacent columns (same
+// residue r) form a cluster.  Each leaves its finished float32 spectrum in its own shared memory in NATURAL
+// order (aliasing the column storage: needs one finished block per thread); after a cluster barrier CTA c
+// writes frequencies [c m/C, (c+1) m/C) of all C columns - a warp reads 128-byte runs from each peer through
+// distributed shared memory and stores C x 8-byte runs instead of single 8-byte pieces.
+template <int BLK>
+__device__ __forceinline__ void finish_and_stage(sc* __restrict__ s, const FftGeom& g, int r, const ScaleOnly& post) {
+  const int n_blocks = g.m / BLK, b = threadIdx.x;
+  const bool have = b < n_blocks;
+  cd x[BLK];
+  if (have) {
+#pragma unroll
+    for (int e = 0; e < BLK; ++e) x[e] = to_cd(s[phys(b * BLK + e)]);
+    finish_block<BLK>(x);
+  }
+  __syncthreads();                                     // every block is in registers: the storage can be reused
+  if (have) {
+    float2* stage = reinterpret_cast<float2*>(s);
+    const int f0 = block_base_frequency(b, g);
+#pragma unroll
+    for (int e = 0; e < BLK; ++e) {
+      const int fp = f0 + n_blocks * block_rev<BLK>(e);
+      float2 S = make_float2(0.f, 0.f);
+      post(fp * g.R + r, x[e], S);
+      stage[fp] = S;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kFftThreads, kFftMinCtas) fft_sed_cluster_kernel(SedArgs a, FftGeom g, int n_cols) {
+  extern __shared__ sc s_data[];
+  const ScaleOnly post{a.inv_n_t};
+  const int C = (int)cluster_size(), rank = (int)cluster_rank();
+  const int r = (blockIdx.x / C) % g.R;
+  const int col0 = (blockIdx.x / (C * g.R)) * C, col = col0 + rank;
+  if (col < n_cols) {
+    FetchPlanar fetch;
+    column_rows(a, 0, col / 3, col % 3, fetch.re, fetch.im);
+    load_column(s_data, fetch, g, r);
+    __syncthreads();
+    fft_smem_passes(s_data, g);
+    if (g.pp.blk == 16) finish_and_stage<16>(s_data, g, r, post);
+    else if (g.pp.blk == 8) finish_and_stage<8>(s_data, g, r, post);
+    else finish_and_stage<4>(s_data, g, r, post);
+  }
+  cluster_barrier();                                   // every column of the cluster is staged
+  const int per = g.m / C, shift = 31 - __clz(C), live = min(C, n_cols - col0);
+  const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(s_data);
+  float2* o = reinterpret_cast<float2*>(a.out) + a.k_offset * 3 + col0;
+  const int64_t fstride = a.n_k_total * 3;
+  constexpr int kBatch = 8;
+  for (int i0 = threadIdx.x; i0 < per * C; i0 += kBatch * blockDim.x) {
+    float2 v[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int i = i0 + u * blockDim.x, c = i & (C - 1), fp = rank * per + (i >> shift);
+      if (i < per * C && c < live) v[u] = ld_peer(stage_addr + (uint32_t)fp * 8u, (uint32_t)c);
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int i = i0 + u * blockDim.x, c = i & (C - 1), fp = rank * per + (i >> shift);
+      if (i < per * C && c < live) o[(int64_t)(fp * g.R + r) * fstride + c] = v[u];
+    }
+  }
+  cluster_barrier();                                   // nobody leaves while a peer may still read its stage
+}
+
 // Bluestein leg 1: column -> chirp, zero-pad, forward transform, times the chirp spectrum -> scratch.
 // block -> (column, r), column = (group, k, pol) flattened.
 __global__ void __launch_bounds__(kFftThreads, kFftMinCtas) bluestein_forward_kernel(SedArgs a, FftGeom g, int n_k,
@@ -884,7 +974,26 @@ int launch_fft(const float* P, int64_t n_groups, int64_t group_stride, int64_t n
   if (need == 0) {                                       // power of two: one fused kernel
     FftGeom g = make_geom(n_t, plan);
     const size_t smem = smem_bytes(g, !coherent);
-    if (coherent) {
+    // 3000 columns of 16384 points: 0.790 ms with direct 8-byte stores, 0.769 with pairs, 0.757 with clusters of 4
+    static const int cluster_env = getenv("PSA_FFT_CLUSTER") ? atoi(getenv("PSA_FFT_CLUSTER")) : 4;
+    const int C = (cluster_env == 2 || cluster_env == 4) ? cluster_env : 1;
+    if (coherent && C > 1 && g.m / g.pp.blk <= kFftThreads && g.m % C == 0 && n_k * 3 >= C) {
+      if ((st = allow_smem(fft_sed_cluster_kernel, smem)) != PSA_OK) return st;
+      const int64_t groups = (n_k * 3 + C - 1) / C;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(groups * g.R * C));
+      cfg.blockDim = dim3(kFftThreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = s;
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = (unsigned)C;
+      attr.val.clusterDim.y = 1;
+      attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      PSA_CUDA(cudaLaunchKernelEx(&cfg, fft_sed_cluster_kernel, a, g, (int)(n_k * 3)));
+    } else if (coherent) {
       if ((st = allow_smem(fft_sed_kernel<PSA_MODE_COHERENT>, smem)) != PSA_OK) return st;
       fft_sed_kernel<PSA_MODE_COHERENT><<<(unsigned)(n_k * 3 * g.R), kFftThreads, smem, s>>>(a, g);
     } else {
