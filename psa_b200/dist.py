@@ -111,7 +111,11 @@ def sliced_ingest(calc, proj_groups, local_rows=None, group=None) -> None:
     """
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     eng, dtraj = calc.engine, calc.device_trajectory
-    if dtraj.has_state(proj_groups, calc.use_displacements):     # same call sequence on every rank: same answer
+    # skip only if EVERY rank already holds the state (a rank that computed something on its own must not
+    # leave the others waiting in the chain)
+    ready = torch.tensor([1 if dtraj.has_state(proj_groups, calc.use_displacements) else 0], device=eng.device)
+    dist.all_reduce(ready, op=dist.ReduceOp.MIN, group=group)
+    if int(ready.item()) == 1:
         return
     n_t, n_a = dtraj.n_t, dtraj.n_a
     bounds = [shard_range(n_t, r, world) for r in range(world)]
