@@ -159,11 +159,34 @@ def graphene_case(psa) -> dict:
     return g
 
 
+def dump_cases(psa) -> None:
+    """Text fixtures of the reference's iSED dump writer (src/psa/io/writer.py:139-228): an orthogonal and a
+    triclinic box, written by ``out_to_qdump`` itself from seeded frames (the inputs are regenerated by the test)."""
+    from psa.io.writer import out_to_qdump  # type: ignore
+    for name, box in DUMP_BOXES.items():
+        frames, types = dump_inputs()
+        out_to_qdump(str(OUT / f"dump_{name}.txt"), frames, types, np.array(box, np.float32))
+        print(f"wrote dump_{name}.txt")
+
+
+DUMP_BOXES = {"ortho": [[10.862, 0, 0], [0, 10.862, 0], [0, 0, 21.724]],
+              "triclinic": [[12.3, 1.5, -0.75], [0, 10.6524, 2.25], [0, 0, 20.0]]}
+
+
+def dump_inputs():
+    rng = np.random.default_rng(2024)
+    frames = (rng.random((3, 7, 3)) * 12 - 1).astype(np.float32)
+    frames[1, 2] = [0.0, -0.0, 1e-7]
+    frames[2, 6] = [123456.789, -9.87654321e-5, 3.0]
+    return frames, np.array([1, 2, 1, 2, 3, 1, 2])
+
+
 def main() -> None:
     psa = load_reference()
     if psa is None:
         raise SystemExit("reference tree not found (set PSA_REFERENCE_SRC)")
     OUT.mkdir(parents=True, exist_ok=True)
+    dump_cases(psa)
     env = _env()
     for name, builder in (("si_small", si_case), ("graphene_small", graphene_case)):
         data = builder(psa)

@@ -1,6 +1,8 @@
 """Host-side logic of the drop-in: directions, k-space, group rules, the SED container.
 Mirrors the reference's own unit tests (tests/test_helpers.py, test_sed.py, test_trajectory.py)
 and pins k-paths / k-grids / lattice vectors against the real reference's outputs (tests/golden)."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -231,3 +233,16 @@ def test_mode_validation_needs_no_gpu():
         with pytest.raises(ValueError, match="summation_mode"):
             call(mags, vecs, summation_mode="partially coherent")
     assert calc._engine is None                      # nothing touched the GPU
+
+
+@pytest.mark.parametrize("name", ["ortho", "triclinic"])
+def test_dump_writer_is_byte_identical_to_the_reference(name, tmp_path):
+    """N2: ``write_lammps_dump`` against text written by the reference's own ``out_to_qdump``
+    (reference: src/psa/io/writer.py:139-228; fixtures from oracle/make_golden.py:dump_cases)."""
+    from oracle.make_golden import DUMP_BOXES, dump_inputs
+    from psa_b200.dump import write_lammps_dump
+    frames, types = dump_inputs()
+    out = tmp_path / "d.dump"
+    write_lammps_dump(str(out), frames, types, np.array(DUMP_BOXES[name], np.float32))
+    want = (Path(__file__).parent / "golden" / f"dump_{name}.txt").read_bytes()
+    assert out.read_bytes() == want
