@@ -265,8 +265,10 @@ __device__ __forceinline__ void smem_butterfly(sc* __restrict__ s, int b, int q,
   for (int i = 0; i < RADIX; ++i) s[kPow2 ? pp0 + i * qs : phys(p0 + i * q)] = to_sc(a[i]);
 }
 
+// One body per (radix, index mode) in the binary: the pass schedule is unrolled over six slots and would otherwise
+// inline sixty butterfly loops (the fused kernel grew to 480 KB of SASS and stalled on instruction fetch).
 template <int RADIX, bool kPow2>
-__device__ __forceinline__ void smem_pass_impl(sc* __restrict__ s, int m, int q, const double2* __restrict__ tab) {
+__device__ __noinline__ void smem_pass_impl(sc* __restrict__ s, int m, int q, const double2* __restrict__ tab) {
   const int n_bfly = m / RADIX, step = blockDim.x;
   if (n_bfly % step == 0) {                            // uniform trip count: no exit test between iterations
     const int per_thread = n_bfly / step;
