@@ -66,3 +66,34 @@ def test_product_code_never_imports_the_oracle():
     for path in (ROOT / "psa_b200").rglob("*.py"):
         text = path.read_text()
         assert "oracle" not in re.sub(r'""".*?"""', "", text, flags=re.S).replace("# oracle", ""), path
+
+
+def test_fft_planner_needs_no_gpu(lib):
+    """Which frame counts take the mixed-radix core (no workspace) and which fall back to Bluestein is decided on
+    the host: n = R * m with m = 4 * 2^a 3^b 5^c <= 4096 and R <= 256 is direct (R is a load-time split, so 28 =
+    7 * 4 qualifies), anything else needs the chirp scratch (8 bytes x 3 n_k x M, M = 2^s >= 2n-1)."""
+    direct = [4, 8, 12, 16, 20, 28, 48, 60, 1000, 1200, 3000, 4096, 10000, 12288, 16384, 20000, 50000, 65536, 2 ** 19]
+    for n in direct:
+        assert lib.psa_fft_workspace_bytes(n, 7, 2) == 0, n
+        assert lib.psa_fft_plan_bytes(n) >= 16 * n, n
+    for n, m in ((2, 32), (7, 32), (250, 512), (3001, 8192), (8191, 16384), (4 * 2503, 32768), (10001, 32768)):
+        assert lib.psa_fft_workspace_bytes(n, 7, 2) == 2 * 7 * 3 * m * 8, n
+        assert lib.psa_fft_plan_bytes(n) >= 16 * (3 * m + n), n
+    for bad in (0, 1, 2 ** 19 + 1):
+        assert lib.psa_fft_plan_bytes(bad) == -1
+
+
+def test_balanced_digit_byte_trick():
+    """The digitiser's carry-free digit extraction: the bytes of (X + 0x808080) ^ 0x808080 are the balanced
+    base-256 digits of X for |X| <= 2^30 (csrc/ingest.cu: quad_words)."""
+    import sys
+
+    import numpy as np
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    import intmodel as M
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.integers(-2 ** 30, 2 ** 30 + 1, 200000),
+                        [2 ** 30, -2 ** 30, 0, 127, 128, -128, -129, 32767, 32768, -32768, -32769, 8388607, 8388608]])
+    z = ((x + 0x00808080) & 0xFFFFFFFF) ^ 0x00808080
+    digits = np.stack([(((z >> (8 * i)) & 0xFF) + 128) % 256 - 128 for i in range(4)]).astype(np.int8)
+    np.testing.assert_array_equal(digits, M.balanced_digits(x.astype(np.int64)))
