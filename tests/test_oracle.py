@@ -139,3 +139,51 @@ def test_parity_report_shape():
     rep = O.parity_report(i_ref * (1 + 1e-7), i_ref, i_ref.astype(np.float64))
     assert rep["global_peak_equal"] and rep["per_k_peak_equal"]
     assert rep[1e-6]["new_ref"]["max"] < 1e-6
+
+
+# ------------------------------------------------------------------ randomized differential check (build container only)
+def _random_case(seed):
+    rng = np.random.default_rng(seed)
+    n_t = int(rng.choice([7, 16, 30, 64, 100, 129]))
+    n_a = int(rng.integers(3, 40))
+    cells = tuple(int(c) for c in rng.integers(1, 4, 3))
+    box = np.diag(rng.uniform(8.0, 25.0, 3)).astype(np.float32)
+    if seed % 2:
+        box[0, 1], box[0, 2], box[1, 2] = rng.uniform(-2, 2, 3).astype(np.float32)     # tilted cell
+    pos = (rng.random((n_t, n_a, 3)) * 20 + rng.standard_normal((n_t, n_a, 3)) * 0.05).astype(np.float32)
+    vel = rng.standard_normal((n_t, n_a, 3)).astype(np.float32)
+    types = rng.integers(1, 4, n_a)
+    kw = [dict(), dict(summation_mode="incoherent"), dict(basis_atom_types=[1, 2], summation_mode="incoherent"),
+          dict(basis_atom_types=[2, 3], summation_mode="coherent"), dict(basis_atom_types=[[1], [2, 3]], summation_mode="incoherent"),
+          dict(basis_atom_indices=[[0, 1], [2]], summation_mode="incoherent"),
+          dict(basis_atom_indices=list(map(int, rng.choice(n_a, 3, replace=False))))][seed % 7]
+    direction = [[1, 0, 0], [1, 1, 0], [1, 1, 1], [0, 1, 2]][seed % 4]
+    return pos, vel, types, box, cells, float(rng.choice([0.001, 0.002, 0.005])), kw, direction, bool(seed % 3 == 0)
+
+
+@pytest.mark.parametrize("seed", range(14))
+def test_oracle_equals_the_real_reference_on_random_inputs(seed):
+    """Seeded random trajectories, cells (incl. tilted), group rules, modes and frame counts (odd and not a power of
+    two): the oracle's k-path and SED equal the imported reference bit for bit.  Skipped where /root/reference is
+    absent (the GPU box)."""
+    from oracle.ref_import import load_reference
+    psa = load_reference()
+    if psa is None:
+        pytest.skip("reference tree not on this machine")
+    pos, vel, types, box, cells, dt, kw, direction, disp = _random_case(seed)
+    n_t = pos.shape[0]
+    traj = psa.Trajectory(pos, vel, types, np.arange(n_t), box, np.diag(box).copy(),
+                          np.array([box[0, 1], box[0, 2], box[1, 2]], np.float32), dt)
+    calc = psa.SEDCalculator(traj, *cells, use_displacements=disp)
+    mags, kv = calc.get_k_path(direction, 2.5, 9)
+    ref = calc.calculate(mags, kv, **kw)
+    new = O.calculate(pos, vel, types, dt, kv, use_displacements=disp, **kw)
+    assert new["is_complex"] == ref.is_complex and new["sed"].dtype == ref.sed.dtype
+    np.testing.assert_array_equal(new["sed"], ref.sed)
+    np.testing.assert_array_equal(new["freqs"], ref.freqs)
+    # host-side k-path of the drop-in, same inputs
+    from psa_b200 import kspace
+    lat = kspace.Lattice.from_box(box, *cells)
+    m2, kv2 = kspace.k_path(lat, direction, 2.5, 9, None)
+    np.testing.assert_array_equal(m2, mags)
+    np.testing.assert_array_equal(kv2, kv)
