@@ -187,3 +187,44 @@ def test_oracle_equals_the_real_reference_on_random_inputs(seed):
     m2, kv2 = kspace.k_path(lat, direction, 2.5, 9, None)
     np.testing.assert_array_equal(m2, mags)
     np.testing.assert_array_equal(kv2, kv)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_oracle_ised_and_chiral_equal_the_real_reference_on_random_inputs(seed):
+    """iSED frames (flat type list = one group per type, index lists, 'auto' and numeric rescale) and the three
+    chiral-phase options on random inputs, oracle vs the imported reference, bit for bit."""
+    from oracle.ref_import import load_reference
+    psa = load_reference()
+    if psa is None:
+        pytest.skip("reference tree not on this machine")
+    from oracle.make_golden import _ised_frames
+    from psa_b200 import kspace
+    pos, vel, types, box, cells, dt, _, _, _ = _random_case(100 + seed)
+    n_t, n_a = pos.shape[:2]
+    traj = psa.Trajectory(pos, vel, types, np.arange(n_t), box, np.diag(box).copy(),
+                          np.array([box[0, 1], box[0, 2], box[1, 2]], np.float32), dt)
+    calc = psa.SEDCalculator(traj, *cells)
+    rng = np.random.default_rng(seed)
+    # chiral phase
+    z1 = (rng.standard_normal((6, 5)) + 1j * rng.standard_normal((6, 5))).astype(np.complex64)
+    z2 = (rng.standard_normal((6, 5)) + 1j * rng.standard_normal((6, 5))).astype(np.complex64)
+    z2[0, 0] = 0
+    for opt in "ABC":
+        np.testing.assert_array_equal(O.chiral_phase(z1, z2, opt), calc.calculate_chiral_phase(z1, z2, opt), err_msg=opt)
+    # iSED
+    direction = [[1, 0, 0], [1, 1, 0]][seed % 2]
+    char_len, nk = 5.0 + seed, 7
+    spec = [dict(basis_atom_types_ised=[1, 2]), dict(basis_atom_idx_ised=[[0, 1], [2]]), dict()][seed % 3]
+    rescale = ["auto", 0.5, 2][seed % 3]
+    k_target, w_target = 0.4 + 0.1 * seed, 20.0 + 10 * seed
+    want = _ised_frames(psa, calc, k_dir_spec=direction, k_target=k_target, w_target=w_target,
+                        char_len_k_path=char_len, nk_on_path=nk, bz_cov_ised=1.0, rescale_factor=rescale,
+                        n_recon_frames=5, **spec)
+    from psa_b200 import groups as G
+    from psa_b200 import parse_direction
+    k_hat = parse_direction(direction)
+    lat = kspace.Lattice.from_box(box, *cells)
+    mags, vecs = kspace.k_path(lat, k_hat, 1.0, nk, char_len)
+    groups = G.resolve_ised_groups(types, n_a, spec.get("basis_atom_idx_ised"), spec.get("basis_atom_types_ised"))
+    got = O.ised(pos, vel, types, dt, k_hat, mags, vecs, k_target, w_target, groups, rescale_factor=rescale, n_frames=5)
+    np.testing.assert_array_equal(got["frames"], want)
