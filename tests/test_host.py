@@ -246,3 +246,35 @@ def test_dump_writer_is_byte_identical_to_the_reference(name, tmp_path):
     write_lammps_dump(str(out), frames, types, np.array(DUMP_BOXES[name], np.float32))
     want = (Path(__file__).parent / "golden" / f"dump_{name}.txt").read_bytes()
     assert out.read_bytes() == want
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_lattice_and_k_grid_equal_the_real_reference_on_random_inputs(seed):
+    """Primitive / reciprocal vectors for random (tilted) cells and k-grids on every plane, against the imported
+    reference, bit for bit.  Skipped where /root/reference is absent."""
+    from oracle.ref_import import load_reference
+    psa = load_reference()
+    if psa is None:
+        pytest.skip("reference tree not on this machine")
+    rng = np.random.default_rng(seed)
+    box = np.diag(rng.uniform(6.0, 30.0, 3)).astype(np.float32)
+    box[0, 1], box[0, 2], box[1, 2] = rng.uniform(-3, 3, 3).astype(np.float32)
+    cells = tuple(int(c) for c in rng.integers(1, 6, 3))
+    n_t, n_a = 4, 3
+    z = np.zeros((n_t, n_a, 3), np.float32)
+    traj = psa.Trajectory(z, z, np.ones(n_a, int), np.arange(n_t), box, np.diag(box).copy(),
+                          np.array([box[0, 1], box[0, 2], box[1, 2]], np.float32), 0.002)
+    ref = psa.SEDCalculator(traj, *cells)
+    lat = kspace.Lattice.from_box(box, *cells)
+    for name in ("a1", "a2", "a3", "b1", "b2", "b3", "recip_vecs_prim"):
+        a, b = getattr(lat, name), getattr(ref, name)
+        assert a.dtype == b.dtype, name
+        np.testing.assert_array_equal(a, b, err_msg=name)
+    plane = ["xy", "yz", "zx"][seed % 3]
+    rx, ry = tuple(rng.uniform(-4, 4, 2)), tuple(rng.uniform(-4, 4, 2))
+    nkx, nky, kfix = int(rng.integers(1, 6)), int(rng.integers(1, 6)), float(rng.uniform(-1, 1))
+    want = ref.get_k_grid(plane, rx, ry, nkx, nky, kfix)
+    got = kspace.k_grid(plane, rx, ry, nkx, nky, kfix)
+    assert got[2] == want[2] and got[0].dtype == want[0].dtype and got[1].dtype == want[1].dtype
+    np.testing.assert_array_equal(got[0], want[0])
+    np.testing.assert_array_equal(got[1], want[1])
