@@ -1,21 +1,25 @@
 #!/usr/bin/env python
-"""Headline benchmark of the SED hot path (contract: see the task brief / DESIGN.md section 6).
+"""Headline benchmark of the SED hot path (contract: see the task brief / DESIGN.md section 5).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1..c5] [--impl reference]
 
 One *step* = one full pass of the hot path over one synthetic trajectory of the named BASELINE.json
 config: mean positions -> digit planes -> (per k-chunk) phase table -> tensor-core projection -> FFT +
-assembly.  ``value`` times that with the raw float32 trajectory already resident in HBM; ``e2e`` times
-the public ``SEDCalculator.calculate`` call on HOST (pinned) arrays: H2D of positions + velocities,
-the same kernels, D2H of the result.  Units are (k-point, timestep, atom) triples per second.
+assembly.  The default workload is ``configs[3]`` (C4: the 100 x 100 k-grid on Si 12x12x12, 16384 frames) -
+the largest configuration BASELINE.json names for 1/2/4/8 GPUs.  Units are (k-point, timestep, atom) triples/s.
 
-N > 1 (launched by torchrun, one rank per GPU): ``value`` is weak scaling - every rank holds the
-trajectory and projects its own n_k k-points of an N x n_k path, no collective in the data path;
-``e2e`` is the real multi-GPU call (rank 0 uploads and ingests, one NCCL broadcast of the digit
-planes, k-sharded compute, gather on rank 0, D2H).
-
-``--impl reference`` times the reference's CPU algorithm (the NumPy oracle port - the reference is
-pure Python and cannot travel to the GPU box) on all host cores, on a bounded k-subset of the workload.
+* ``value``: inputs already resident in HBM.  N = 1: the raw float32 trajectory is on the device, the result stays
+  there.  N > 1 (torchrun, one rank per GPU): STRONG scaling of the same job - the frames are resident in HBM spread
+  over the ranks (rank r holds frames ``shard_range(n_t, r, N)``), every step runs the sliced ingest (ordered float32
+  mean chain rank to rank, every rank's digitise kernel storing its rows into all ranks' digit planes through
+  NVLink, two one-element all-reduces as stream fences) and then each rank projects + transforms its 1/N of the
+  k-points.  The collectives inside the timed region are exactly those.
+* ``e2e``: the public call on HOST (pinned) arrays - ``SEDCalculator.calculate`` (N = 1) or
+  ``psa_b200.dist.calculate_sharded(ingest="sliced")`` (N > 1): H2D of positions + velocities (1/N per rank over its
+  own PCIe link), the same kernels and exchange, D2H of every rank's spectra into one shared pinned host array.
+* ``--impl reference`` times the reference's CPU algorithm (the NumPy oracle port, pinned bit for bit to the
+  reference; the reference itself is pure Python and does not travel to the GPU box) with all host threads, on a
+  bounded k-subset of the same workload per step.
 """
 from __future__ import annotations
 
@@ -28,14 +32,30 @@ import threading
 import time
 from pathlib import Path
 
-import numpy as np
+
+def _host_cpus() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm must use all host cores, and BLAS reads these
+# variables when NumPy is first imported - so this has to happen before `import numpy`.
+if "reference" in sys.argv:
+    for _var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_var] = str(_host_cpus())
+
+import numpy as np  # noqa: E402
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "k-points\u00b7timesteps\u00b7atoms/sec"      # BASELINE.json's metric, verbatim
+METRIC = "k-points·timesteps·atoms/sec"      # BASELINE.json's metric, verbatim
 UNIT = "k*t*atom/s"
 FLOP_PER_UNIT = 12.0          # 3 pol x (2 mul + 2 add): real series x complex phase
+DEFAULT_WORKLOAD = "c4"
+CPU_K = {"c1": 100, "c2": 200, "c3": 80, "c4": 48, "c5": 6}     # k-points per CPU-arm step (C1-C3: the full k-set)
 
 
 def log(*a):
@@ -53,25 +73,29 @@ def emit(line: dict) -> None:
     _REAL_STDOUT.flush()
 
 
+def config_of(args, cfg) -> dict:
+    """The ``config`` object - identical in both arms (the driver compares them)."""
+    return {"workload": args.workload, "desc": cfg["desc"]}
+
+
 # ------------------------------------------------------------------------------------------------ workload
-def build_jobs(cfg, calc, k_mult=1):
-    """[(k_mags, k_vecs, kwargs, chiral_pair|None)] for one step of the config; ``k_mult`` densifies
-    the k-set (weak scaling over ranks)."""
+def build_jobs(cfg, calc):
+    """[(k_mags, k_vecs, kwargs, chiral_pair|None)] for one step of the config."""
     jobs = []
     common = dict(basis_atom_types=cfg.get("basis_atom_types"), summation_mode=cfg["summation_mode"])
     if cfg["kind"] in ("kpath", "chiral"):
         for path in cfg["paths"]:
-            mags, vecs = calc.get_k_path(path["direction"], cfg["bz_coverage"], path["n_k"] * k_mult)
+            mags, vecs = calc.get_k_path(path["direction"], cfg["bz_coverage"], path["n_k"])
             pair = (0, 1) if cfg["kind"] == "chiral" else None
             jobs.append((mags, vecs, dict(common), pair))
     else:
         kr = cfg["k_ranges"]
-        mags, vecs, shape = calc.get_k_grid(cfg["plane"], kr[:2], kr[2:], cfg["n_kx"] * k_mult, cfg["n_ky"], cfg["k_fixed"])
+        mags, vecs, shape = calc.get_k_grid(cfg["plane"], kr[:2], kr[2:], cfg["n_kx"], cfg["n_ky"], cfg["k_fixed"])
         jobs.append((mags, vecs, dict(common), None))
     return jobs
 
 
-def units_of(cfg, types, n_t, jobs_slices):
+def units_of(types, n_t, jobs_slices):
     """(k, t, atom) triples of a step: sum over jobs and projected groups of n_k * n_t * n_atoms_group."""
     from psa_b200 import groups as grp
     total = 0
@@ -82,13 +106,14 @@ def units_of(cfg, types, n_t, jobs_slices):
     return total
 
 
-def pinned_trajectory(spec):
+def pinned_frames(spec, f0, f1):
+    """Frames [f0, f1) of the synthetic trajectory in pinned host memory."""
     import torch
-    shape = (spec.n_frames, spec.n_atoms, 3)
+    shape = (f1 - f0, spec.n_atoms, 3)
     pos = torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()
     vel = torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()
-    spec.frames(0, spec.n_frames, out_pos=pos, out_vel=vel, threads=min(16, os.cpu_count() or 8))
-    return spec.wrap(pos, vel)
+    spec.frames(f0, f1, out_pos=pos, out_vel=vel, threads=min(16, _host_cpus()))
+    return pos, vel
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -131,7 +156,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_sample(cfg, traj, max_k=48, repeats=1):
+def cpu_sample(cfg, traj, max_k):
     """Oracle (NumPy port of the reference, all host cores) on a bounded k-subset; returns (units/s, desc, s)."""
     from oracle import psa_oracle as O
     from psa_b200 import kspace
@@ -144,18 +169,16 @@ def cpu_sample(cfg, traj, max_k=48, repeats=1):
         _, vecs = kspace.k_path(lat, p["direction"], cfg["bz_coverage"], p["n_k"])
     sel = np.linspace(0, len(vecs) - 1, min(max_k, len(vecs))).round().astype(int)
     kv = np.ascontiguousarray(vecs[sel])
-    best = float("inf")
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        res = O.calculate(traj.positions, traj.velocities, traj.types, traj.dt_ps, kv,
-                          basis_atom_types=cfg.get("basis_atom_types"), summation_mode=cfg["summation_mode"])
-        best = min(best, time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    res = O.calculate(traj.positions, traj.velocities, traj.types, traj.dt_ps, kv,
+                      basis_atom_types=cfg.get("basis_atom_types"), summation_mode=cfg["summation_mode"])
+    sec = time.perf_counter() - t0
     n_atoms = sum(int(g.size) for g in res["groups"]) if not res["is_complex"] else \
         int(np.unique(np.concatenate(res["groups"])).size)
     units = len(kv) * traj.n_frames * n_atoms
     desc = (f"{len(kv)} of {len(vecs)} k-points of {cfg['spec'].name} ({traj.n_frames} frames x {n_atoms} atoms), "
             f"full trajectory, one calculate() incl. mean/phase/einsum/FFT")
-    return units / best, desc, best
+    return units / sec, desc, sec
 
 
 def host_threads():
@@ -166,30 +189,32 @@ def host_threads():
             return max(n)
     except Exception:
         pass
-    return os.cpu_count() or 1
+    return _host_cpus()
 
 
 def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    traj = cfg["spec"].trajectory(threads=min(16, os.cpu_count() or 8))
+    traj = cfg["spec"].trajectory(threads=min(16, _host_cpus()))
+    max_k = args.cpu_k or CPU_K.get(args.workload, 48)
     for _ in range(args.warmup):
-        cpu_sample(cfg, traj, max_k=8)
+        cpu_sample(cfg, traj, max_k=min(8, max_k))
     rates, desc = [], ""
     t_begin = time.perf_counter()
     for _ in range(args.steps):
-        val, desc, _sec = cpu_sample(cfg, traj, max_k=args.cpu_k)
+        val, desc, _sec = cpu_sample(cfg, traj, max_k=max_k)
         rates.append(val)
     ms = 1e3 * (time.perf_counter() - t_begin) / args.steps
     units_per_s = float(np.median(rates))
     cores = host_threads()
     line = {"impl": "reference", "metric": METRIC, "value": units_per_s, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "desc": cfg["desc"], "inputs": "host memory"},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_of(args, cfg),
             "cpu_baseline": {"value": units_per_s, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": units_per_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "details": {"inputs": "host memory", "omp_num_threads": os.environ.get("OMP_NUM_THREADS")},
             "gpu_launches": 0}
     emit(line)
 
@@ -199,23 +224,70 @@ def peaks():
     path = ROOT / "MEASURED_PEAKS.json"
     if path.exists():
         p = json.loads(path.read_text())
-        return p["hbm_gbs"], p["bf16_tflops"], "measured (MEASURED_PEAKS.json)"
-    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+        return (p["hbm_gbs"], p["bf16_tflops"], p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "measured (MEASURED_PEAKS.json)")
+    return 6650.0, 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
-def roofline_for(kernel, ms_total, calls, work, traffic):
-    """``work`` = algorithmic bytes or flops per step for that kernel (see DESIGN.md section 5)."""
-    hbm, tf, which = peaks()
+def measure_int8_peak(dev):
+    """Dense int8 tensor throughput of this GPU with the driver's own methodology for bf16 (torch, 8192^3: best of 10
+    = burst, back to back for 4 s = sustained), through cuBLASLt's int8 GEMM.  None when the library path is missing."""
+    import torch
+    try:
+        n = 8192
+        a = torch.randint(-100, 100, (n, n), dtype=torch.int8, device=dev)
+        b = torch.randint(-100, 100, (n, n), dtype=torch.int8, device=dev)
+        for _ in range(3):
+            torch._int_mm(a, b)
+        torch.cuda.synchronize(dev)
+        best = float("inf")
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch._int_mm(a, b)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        ops = 2.0 * n ** 3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_end, reps = time.time() + 4.0, 0
+        e0.record()
+        while time.time() < t_end:
+            for _ in range(20):
+                torch._int_mm(a, b)
+            reps += 20
+            torch.cuda.synchronize(dev)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return {"int8_tops": ops / (best / 1e3) / 1e12,
+                "int8_tops_sustained": ops * reps / (e0.elapsed_time(e1) / 1e3) / 1e12,
+                "how": "torch._int_mm int8 8192^3 (2*N^3): best of 10 (burst) and back to back for 4 s (sustained)"}
+    except Exception as exc:
+        log(f"[bench] int8 peak not measured: {exc}")
+        return None
+
+
+def roofline_for(kernel, ms_total, calls, work, traffic, int8_peak=None, long_step=False):
+    """``work`` = algorithmic bytes or flops per step for that kernel (see DESIGN.md section 4)."""
+    hbm, tf_burst, tf_sust, which = peaks()
     per_launch_s = ms_total / 1e3 / max(calls, 1)
     if kernel == "psa_project":
+        tf = tf_sust if long_step else tf_burst
         ach = work / max(calls, 1) / per_launch_s / 1e12
+        if int8_peak:
+            ipeak = int8_peak["int8_tops_sustained" if long_step else "int8_tops"]
+            isrc = "measured in this run: " + int8_peak["how"]
+        else:
+            ipeak, isrc = 2.0 * tf, "ASSUMED 2 x the measured dense bf16 peak (int8 GEMM not available to measure)"
         return {"kernel": kernel, "bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s",
-                "frac": ach / tf, "traffic": traffic, "peak_source": which,
+                "frac": ach / tf, "traffic": traffic,
+                "peak_source": which + (" sustained" if long_step else " burst"),
                 # the same launch counted in the int8 operations the tensor cores actually execute
-                "executed": {"achieved": 10.0 * ach, "peak": 2.0 * tf, "unit": "int8 TOP/s", "frac": 10.0 * ach / (2.0 * tf),
-                             "peak_source": "2 x the measured dense bf16 peak (int8 runs at twice the bf16 rate)"},
-                "note": "algorithmic 12 flop/unit; executed: 10 int8 digit products per MAC (120 int8-op/unit), "
-                        "so frac <= 2*bf16_peak/10 by construction; see ncu tensor-pipe utilisation in profiles/"}
+                "executed": {"achieved": 10.0 * ach, "peak": ipeak, "unit": "int8 TOP/s", "frac": 10.0 * ach / ipeak,
+                             "peak_source": isrc},
+                "note": "algorithmic 12 flop/unit; executed: 10 exact int8 digit products per MAC (120 int8-op/unit), "
+                        "so the algorithmic frac is <= int8_peak/(10*bf16_peak) by construction; ncu tensor-pipe "
+                        "utilisation in profiles/"}
     ach = work / max(calls, 1) / per_launch_s / 1e9
     return {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
             "traffic": traffic, "peak_source": which}
@@ -238,15 +310,19 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="psa_b200", choices=["psa_b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("PSA_BENCH_WORKLOAD", "c2"))
+    ap.add_argument("--workload", default=os.environ.get("PSA_BENCH_WORKLOAD", DEFAULT_WORKLOAD))
     ap.add_argument("--frames", type=int, default=None, help="override n_frames (smoke runs only)")
-    ap.add_argument("--cpu-k", type=int, default=100, help="k-points in the CPU baseline sample")
+    ap.add_argument("--cells", type=int, default=None, help="override the supercell size (smoke runs only)")
+    ap.add_argument("--cpu-k", type=int, default=None, help="k-points in one CPU-arm step (default: per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ised", action="store_true")
+    ap.add_argument("--no-int8-peak", action="store_true")
     args = ap.parse_args()
+    args.workload = args.workload.lower()
 
-    from psa_b200 import synth
-    cfg = synth.baseline_config(args.workload, n_frames=args.frames)
+    import synthetic as synth
+    cfg = synth.baseline_config(args.workload, n_frames=args.frames, n_cells=args.cells)
     spec = cfg["spec"]
     cfg["desc"] = (f"{spec.name}: {spec.n_atoms} atoms x {spec.n_frames} frames, {cfg['kind']}, "
                    f"{cfg['summation_mode']}, basis_atom_types={cfg.get('basis_atom_types')}")
@@ -257,6 +333,7 @@ def main():
     import torch.distributed as dist
     from psa_b200 import SEDCalculator
     from psa_b200 import dist as pdist
+    from psa_b200 import groups as grp
 
     rank, world, local = pdist.init_from_env()
     if world != args.gpus:
@@ -268,40 +345,44 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # Every rank needs the raw trajectory resident in HBM for the weak-scaling `value`.  Small workloads are
-    # generated by every rank (same seed); large ones are generated once on rank 0 and copied GPU-to-GPU
-    # (setup, untimed) so that host memory holds one copy only.
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- inputs.  N = 1: the whole trajectory (pinned host + device).  N > 1: this rank's frames only.
     t_gen = time.time()
-    traj_bytes = 2 * spec.n_frames * spec.n_atoms * 12
-    share = world > 1 and traj_bytes > (4 << 30)
-    resident = None
-    if rank == 0 or not share:
-        traj = pinned_trajectory(spec)
-    else:
-        zero = np.broadcast_to(np.zeros(1, np.float32), (spec.n_frames, spec.n_atoms, 3))
+    n_t, n_a = spec.n_frames, spec.n_atoms
+    f0, f1 = pdist.shard_range(n_t, rank, world)
+    if world > 1 and f0 % synth.BLOCK:
+        raise SystemExit(f"[bench] {n_t} frames do not split over {world} ranks on {synth.BLOCK}-frame blocks")
+    pos_rows, vel_rows = pinned_frames(spec, f0, f1)
+    if world == 1:
+        traj = spec.wrap(pos_rows, vel_rows)
+    else:           # shape-only placeholder: the sharded calls take this rank's rows explicitly
+        zero = np.broadcast_to(np.zeros(1, np.float32), (n_t, n_a, 3))
         traj = spec.wrap(zero, zero)
-    log(f"[bench r{rank}] generated {cfg['desc']} in {time.time() - t_gen:.1f}s (shared={share})")
+    log(f"[bench r{rank}] generated frames [{f0}, {f1}) of {cfg['desc']} in {time.time() - t_gen:.1f}s")
     calc = SEDCalculator(traj, *spec.cells, device=dev.index)
     eng = calc.engine
-    if share:
-        from psa_b200.engine import DeviceTrajectory
-        shape = (spec.n_frames, spec.n_atoms, 3)
-        resident = []
-        for arr in (traj.positions, traj.velocities):
-            t = torch.empty(shape, dtype=torch.float32, device=dev)
-            if rank == 0:
-                t.copy_(torch.from_numpy(arr), non_blocking=True)
-            dist.broadcast(t, src=0)
-            resident.append(t)
-        calc._dev_traj = DeviceTrajectory(eng, resident[0], resident[1])
-    jobs = build_jobs(cfg, calc, k_mult=world)
+    jobs = build_jobs(cfg, calc)
     slices = [pdist.shard_range(len(j[1]), rank, world) for j in jobs]
+    rows_dev = None
+    if world > 1:
+        rows_dev = (torch.from_numpy(pos_rows).to(dev), torch.from_numpy(vel_rows).to(dev))     # resident, untimed
+
+    def proj_groups_of(kw):
+        g = grp.resolve_sed_groups(traj.types, n_a, None, kw["basis_atom_types"], kw["summation_mode"])
+        return grp.plan_sed_groups(g, kw["summation_mode"])
 
     def step_resident():
-        """Hot path from the raw device-resident trajectory to the device-resident result."""
+        """Hot path from the device-resident raw frames to the device-resident result (this rank's k-slice)."""
         calc.device_trajectory.reset_derived()
         outs = []
         for (mags, vecs, kw, pair), (k0, k1) in zip(jobs, slices):
+            if world > 1:
+                pdist.sliced_ingest(calc, proj_groups_of(kw)[1], rows_dev)
             out, _, _ = calc._calculate_device(vecs[k0:k1], None, kw["basis_atom_types"], kw["summation_mode"])
             if pair is not None:
                 outs.append(calc._chiral_phase_of_result(out, pair))
@@ -309,7 +390,8 @@ def main():
         return outs
 
     # ---------------- value: inputs resident in HBM
-    _ = calc.device_trajectory.positions, calc.device_trajectory.velocities     # upload once, untimed
+    if world == 1:
+        _ = calc.device_trajectory.positions, calc.device_trajectory.velocities     # upload once, untimed
     for _ in range(args.warmup):
         step_resident()
     barrier()
@@ -325,18 +407,13 @@ def main():
     barrier()
     t1 = time.time()
     clocks = sampler.stop(t0, t1)
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms.item()) / args.steps
+    ms_per_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
     launches = eng.launches - launches0                         # this rank's kernels inside the timed region
 
-    units_local = units_of(cfg, traj.types, traj.n_frames, list(zip(jobs, slices)))
-    units_t = torch.tensor([float(units_local)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(units_t, op=dist.ReduceOp.SUM)
-    units = float(units_t.item())
-    value = units / (ms_per_step / 1e3)
+    jobs_full = [(j, (0, len(j[1]))) for j in jobs]
+    units_total = float(units_of(traj.types, n_t, jobs_full))   # the whole job, whatever N
+    units_local = float(units_of(traj.types, n_t, list(zip(jobs, slices))))
+    value = units_total / (ms_per_step / 1e3)
 
     # ---------------- per-kernel breakdown (one extra step, events around every C-ABI call)
     eng.profile = {}
@@ -344,52 +421,37 @@ def main():
     prof = eng.profile_summary()
     eng.profile = None
     total_prof = sum(v["ms"] for v in prof.values()) or 1.0
-    n_t, n_all = traj.n_frames, traj.n_atoms
-    n_sel_units = units_local / max(n_t, 1)                      # sum over jobs/groups of n_k * n_atoms_group
     n_k_local = sum(k1 - k0 for k0, k1 in slices)
-    from psa_b200 import groups as grp
-    g0 = grp.resolve_sed_groups(traj.types, n_all, None, cfg.get("basis_atom_types"), cfg["summation_mode"])
-    cplx, proj_groups = grp.plan_sed_groups(g0, cfg["summation_mode"])
+    cplx, proj_groups = proj_groups_of(jobs[0][2])
     n_sel_sum = sum(int(p.size) for p in proj_groups)
+    rows_local = (f1 - f0) if world > 1 else n_t
     work = {
         "psa_project": FLOP_PER_UNIT * units_local,                                           # flops
-        "psa_mean_positions": 12.0 * n_t * n_all,                                             # bytes
+        "psa_mean_positions": 12.0 * n_t * n_a,                                               # bytes
+        "psa_mean_accumulate": 12.0 * rows_local * n_a,
         "psa_digitize": 24.0 * n_t * n_sel_sum,
-        "psa_phase_digits": 8.0 * n_sel_units / 1.0,
+        "psa_digitize_rows": 24.0 * rows_local * n_sel_sum,
+        "psa_digitize_rows_peers": (12.0 + 12.0 * world) * rows_local * n_sel_sum,           # read once, stored on N ranks
+        "psa_phase_digits": 8.0 * units_local / max(n_t, 1),
         "psa_fft_sed": (48.0 if cplx else 24.0 * len(proj_groups) + 4.0) * n_k_local * n_t,
         "psa_chiral_phase": 20.0 * n_k_local * n_t,
     }
+    long_step = ms_per_step > 20.0          # a step of tens of ms runs under the power cap: sustained peaks apply
+    int8_peak = None if (args.no_int8_peak or rank != 0) else measure_int8_peak(dev)
     kernels = {k: {"ms": v["ms"], "share": v["ms"] / total_prof, "calls": v["calls"]} for k, v in prof.items()}
     dominant = max(prof, key=lambda k: prof[k]["ms"])
-    roof = roofline_for(dominant, prof[dominant]["ms"], prof[dominant]["launches"], work.get(dominant, 0.0),
-                        ncu_traffic(dominant, args.workload))
-    rooflines = {k: roofline_for(k, prof[k]["ms"], prof[k]["launches"], work[k], ncu_traffic(k, args.workload))
-                 for k in prof if k in work}
+    rooflines = {k: roofline_for(k, prof[k]["ms"], prof[k]["launches"], work[k], ncu_traffic(k, args.workload),
+                                 int8_peak, long_step) for k in prof if k in work}
+    roof = rooflines.get(dominant) or roofline_for(dominant, prof[dominant]["ms"], prof[dominant]["launches"], 0.0, None)
 
     # ---------------- e2e: public API on host (pinned) arrays, H2D + compute + D2H inside the timed region
-    e2e = None
+    e2e, parity = None, None
     if not args.no_e2e:
         d2h = [0]
-        # N > 1: every rank uploads its own 1/N of the frames (pinned) over its own PCIe link
-        ingest, local_rows = "broadcast", None
-        if world > 1:
-            f0, f1 = pdist.shard_range(spec.n_frames, rank, world)
-            if not share or rank == 0:
-                ingest = "sliced"
-                local_rows = (traj.positions[f0:f1], traj.velocities[f0:f1])
-            elif f0 % 256 == 0:                              # synthetic frames are generated in blocks of 256
-                ingest = "sliced"
-                rows_shape = (f1 - f0, spec.n_atoms, 3)
-                lp = torch.empty(rows_shape, dtype=torch.float32, pin_memory=True).numpy()
-                lv = torch.empty(rows_shape, dtype=torch.float32, pin_memory=True).numpy()
-                spec.frames(f0, f1, out_pos=lp, out_vel=lv, threads=min(16, os.cpu_count() or 8))
-                local_rows = (lp, lv)
-            flag = torch.tensor([1 if ingest == "sliced" else 0], device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if int(flag.item()) == 0:
-                ingest, local_rows = "broadcast", None
+        stage_ms = {}
+        last = {}
 
-        def step_e2e():
+        def step_e2e(timings=None):
             calc.release_device_memory()
             res_bytes = 0
             for (mags, vecs, kw, pair) in jobs:
@@ -400,88 +462,118 @@ def main():
                     else:
                         res = calc.calculate(mags, vecs, **kw)
                 else:
-                    res = pdist.calculate_sharded(calc, mags, vecs, ingest=ingest, local_rows=local_rows, **kw)
+                    res = pdist.calculate_sharded(calc, mags, vecs, ingest="sliced", local_rows=(pos_rows, vel_rows),
+                                                  timings=timings, **kw)
                 if res is not None:
                     res_bytes += res.sed.nbytes + (res.phase.nbytes if res.phase is not None else 0)
+                    last["res"] = res
             d2h[0] = res_bytes
 
         n_e2e = max(1, min(args.steps, 5))
         for _ in range(min(args.warmup, 2)):
             step_e2e()
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n_e2e):
             step_e2e()
         e1.record()
         barrier()
         wall_ms = 1e3 * (time.perf_counter() - w0) / n_e2e
-        ems = torch.tensor([max(e0.elapsed_time(e1) / n_e2e, wall_ms)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        jobs_full = [(j, (0, len(j[1]))) for j in jobs]
-        units_e2e = units_of(cfg, traj.types, traj.n_frames, jobs_full)
-        e2e = {"value": units_e2e / (float(ems.item()) / 1e3), "unit": UNIT, "ms_per_step": float(ems.item()),
-               "steps": n_e2e, "h2d_bytes_per_step": int(2 * traj.positions.nbytes),
-               "d2h_bytes_per_step": int(d2h[0]),
+        e2e_ms = max_over_ranks(max(e0.elapsed_time(e1) / n_e2e, wall_ms))
+        if world > 1:                                           # one extra, untimed call for the stage breakdown
+            step_e2e(timings=stage_ms)
+            barrier()
+        e2e = {"value": units_total / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+               "steps": n_e2e, "h2d_bytes_per_step": int(2 * n_t * n_a * 12), "d2h_bytes_per_step": int(d2h[0]),
+               "stage_ms_rank0": {k: round(v, 3) for k, v in stage_ms.items()} or None,
                "path": "SEDCalculator.calculate on pinned host arrays" if world == 1 else
-                       ("psa_b200.dist.calculate_sharded(ingest='sliced'): every rank uploads 1/N of the frames, running-sum "
-                        "mean chain + all-gather of the digit planes, k-sharded compute, gather, D2H" if ingest == "sliced" else
-                        "psa_b200.dist.calculate_sharded: rank-0 upload+ingest, NCCL broadcast, k-sharded compute, gather, D2H")}
+                       "psa_b200.dist.calculate_sharded(ingest='sliced'): every rank uploads 1/N of the frames over its own "
+                       "PCIe link, float32 mean chain, digit planes stored into every rank through NVLink by the digitise "
+                       "kernel, k-sharded compute, every rank's spectra copied into one shared pinned host array"}
 
-    # ---------------- batched iSED (configs that name it: C5's 64 (k, omega) points, split over the ranks)
+        # ---------------- multi-GPU parity: a few k columns of the sharded result against a single-GPU compute, bitwise
+        if world > 1:
+            ok = 1
+            if rank == 0:
+                res = last["res"]
+                mags, vecs, kw, pair = jobs[-1]
+                n_k = len(vecs)
+                per = [pdist.shard_range(n_k, r, world) for r in range(world)]
+                cols = sorted({a for a, b in per if b > a} | {b - 1 for a, b in per if b > a}
+                              | {(a + b) // 2 for a, b in per if b > a})
+                t_par = time.time()
+                full = spec.trajectory(threads=min(16, _host_cpus()))
+                single = SEDCalculator(full, *spec.cells, device=dev.index)
+                one = single.calculate(np.zeros(len(cols), np.float32), vecs[cols], **kw)
+                ok = int(np.array_equal(one.sed, res.sed[:, cols]))
+                single.release_device_memory()
+                parity = {"parity_checked": bool(ok), "columns": len(cols), "seconds": round(time.time() - t_par, 1),
+                          "how": "k columns from every rank's slice of the sharded e2e result vs SEDCalculator.calculate on "
+                                 "one GPU with the whole trajectory: numpy.array_equal (bitwise)"}
+                del full, one
+            flag = torch.tensor([ok], device=dev)
+            dist.broadcast(flag, src=0)
+        last.clear()
+
+    # ---------------- batched iSED: 64 (k, omega) points x 100 frames on this trajectory (C5 names it; measured on
+    # every workload at N = 1 so that the driver's record carries the kernel)
     ised = None
-    if cfg.get("ised_points"):
-        n_pts, n_fr = int(cfg["ised_points"]), int(cfg["ised_frames"])
+    if not args.no_ised and world == 1:
+        n_pts, n_fr = int(cfg.get("ised_points", 64)), int(cfg.get("ised_frames", 100))
         side = max(1, int(round(n_pts ** 0.5)))
         a_lat = float(np.linalg.norm(calc.a1))
         k_max = 2.0 * np.pi / a_lat
         targets = [(k_max * (i + 1) / (side + 1), 1.0 + 14.0 * j / max(1, side - 1)) for i in range(side) for j in range(side)]
-        mine = targets[rank::world]
         kw = dict(nk_on_path=100, bz_cov_ised=1.0, n_recon_frames=n_fr)
-        calc.reconstruct([1, 0, 0], mine[:1], a_lat, **kw)                      # warm-up
-
-        def timed(**extra):
-            barrier()
-            t0 = time.perf_counter()
-            out = calc.reconstruct([1, 0, 0], mine, a_lat, **kw, **extra)
-            torch.cuda.synchronize(dev)
-            sec = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(sec, op=dist.ReduceOp.MAX)
-            return out, float(sec.item())
-
-        res, sec_dev = timed(keep_on_device=True)
+        calc.reconstruct([1, 0, 0], targets[:2], a_lat, keep_on_device=True, **kw)      # warm-up (ingest, plans)
+        eng.profile = {}
+        torch.cuda.synchronize(dev)
+        t_i = time.perf_counter()
+        res = calc.reconstruct([1, 0, 0], targets, a_lat, keep_on_device=True, rescale_factor="auto", **kw)
+        torch.cuda.synchronize(dev)
+        sec_dev = time.perf_counter() - t_i
+        iprof = eng.profile_summary()
+        eng.profile = None
         ok = bool(all(torch.isfinite(r["frames"]).all().item() for r in res[:2]))
         del res
-        res, sec_host = timed()
-        out_bytes = 12.0 * len(targets) * n_fr * traj.n_atoms
-        ised = {"points": len(targets), "frames": n_fr, "atoms": int(traj.n_atoms), "frames_GB": out_bytes / 1e9,
-                "seconds_device_resident": sec_dev, "GB_per_s_device_resident": out_bytes / 1e9 / sec_dev,
-                "seconds_to_host": sec_host, "GB_per_s_to_host": out_bytes / 1e9 / sec_host,
-                "path": "SEDCalculator.reconstruct: amplitudes from one projection pass per atom group, frames "
-                        "synthesised on the GPU (left there / copied into fresh host arrays); points split over the ranks",
-                "checked": ok and bool(all(np.isfinite(r["frames"]).all() for r in res[:2]))}
-        del res
+        out_bytes = 12.0 * len(targets) * n_fr * n_a
+        k_ms = iprof.get("psa_ised_frames", {}).get("ms", 0.0)
+        ised = {"points": len(targets), "frames": n_fr, "atoms": int(n_a), "frames_GB": out_bytes / 1e9,
+                "seconds_whole_call_device_resident": sec_dev, "kernel_ms": {k: v["ms"] for k, v in iprof.items()},
+                "path": "SEDCalculator.reconstruct(rescale_factor='auto'): amplitudes from one projection pass per atom "
+                        "group, one batched max pass + one batched synthesis pass over all points", "checked": ok}
+        if k_ms > 0:
+            rooflines["psa_ised_frames"] = roofline_for("psa_ised_frames", k_ms, iprof["psa_ised_frames"]["launches"],
+                                                        out_bytes, None)
 
     # ---------------- CPU baseline (rank 0, N == 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        val, desc, sec = cpu_sample(cfg, traj, max_k=args.cpu_k)
+        val, desc, sec = cpu_sample(cfg, traj, max_k=args.cpu_k or CPU_K.get(args.workload, 48))
         cpu = {"value": val, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": desc, "seconds": sec}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "s8 digit planes -> s32 (exact), f64 FFT", "data": "synthetic",
-            "config": {"workload": args.workload, "desc": cfg["desc"], "k_points_per_gpu": n_k_local,
-                       "l2_policy": "inputs larger than L2 (trajectory %.0f MB per array)" % (traj.positions.nbytes / 1e6),
-                       "step": "mean positions + digit planes + phase table + tcgen05 projection + FFT/assembly"},
+            "config": config_of(args, cfg),
+            "details": {"k_points_total": int(sum(len(j[1]) for j in jobs)), "k_points_this_rank": int(n_k_local),
+                        "frames_resident_this_rank": int(rows_local),
+                        "l2_policy": "inputs larger than L2 (trajectory %.0f MB per array%s)"
+                                     % (n_t * n_a * 12 / 1e6, "" if world == 1 else f", 1/{world} per rank"),
+                        "step": "mean positions + digit planes + phase table + tcgen05 projection + FFT/assembly",
+                        "collectives_in_value": None if world == 1 else
+                        "N-1 send/recv hops + 1 broadcast of the (n_atoms, 3) running mean; digit planes exchanged by the "
+                        "digitise kernel's peer stores (NVLink) between two 1-element all-reduces; nothing during compute"},
             "roofline": roof, "rooflines": rooflines, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "ised": ised,
+            "int8_peak": int8_peak,
             "gpu_launches": int(launches), "gpu_launches_per_step": int(launches) // max(1, args.steps), "clocks": clocks,
         }
+        if parity is not None:
+            line.update(parity_checked=parity["parity_checked"], parity=parity)
         emit(line)
     if world > 1:
         dist.barrier()

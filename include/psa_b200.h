@@ -32,9 +32,8 @@ extern "C" {
 #define PSA_MODE_INCOHERENT 1  /* float32  out[n_f][n_k_total] = sum_groups sum_pol |S|^2 */
 
 /* psa_project() kernels */
-#define PSA_PROJECT_TENSOR 0   /* tcgen05 int8 tensor-core kernel (the product path)      */
-#define PSA_PROJECT_SIMT 1     /* dp4a CUDA-core kernel, same exact result (bring-up/validation) */
-#define PSA_PROJECT_TENSOR_PAIR 2 /* tcgen05 cta_group::2 variant of the tensor-core kernel (same result) */
+#define PSA_PROJECT_TENSOR 0   /* tcgen05 cta_group::2 int8 tensor-core kernel (the product path) */
+#define PSA_PROJECT_SIMT 1     /* dp4a CUDA-core kernel, same exact result (bring-up/validation)  */
 
 int psa_version(void);
 const char* psa_last_error(void);
@@ -55,9 +54,14 @@ int psa_mean_positions(const float* pos, int64_t n_t, int64_t n_a, float* mean, 
  * (reference: sed_calculator.py:69-72).
  *   data [n_t][n_a][3] float32 (velocities, or positions when `mean` != NULL -> displacements)
  *   mean [n_a][3] float32 or NULL      idx [n_sel] int32 atom indices or NULL (= all atoms, n_sel == n_a)
- *   dig  [3 pol][4 slice][n_t][pitch] int8     expo [3][n_t] int32 (row exponent e: |x| < 2^e) */
-int psa_digitize(const float* data, const float* mean, const int32_t* idx, int64_t n_t, int64_t n_a,
-                 int64_t n_sel, int64_t pitch, int8_t* dig, int32_t* expo, void* stream);
+ *   weight [n_a] float32 or NULL: per-atom factor applied in float32 after the mean subtraction - the README
+ *          facade's mass weighting sqrt(m) (reference: README.md:83-101; the shipped source is unweighted = NULL)
+ *   dig  [3 pol][4 slice][n_t][pitch] int8
+ *   expo [3][n_t] int32 (row exponent e: |x| < 2^e).  A row holding NaN / Inf / |x| >= 2^100 gets the poison
+ *        exponent 0x40000000 and zero digits; psa_project turns it into NaN projections (the reference's float
+ *        arithmetic propagates non-finite samples into the spectrum as well). */
+int psa_digitize(const float* data, const float* mean, const float* weight, const int32_t* idx, int64_t n_t,
+                 int64_t n_a, int64_t n_sel, int64_t pitch, int8_t* dig, int32_t* expo, void* stream);
 
 /* The two ingest steps on a contiguous range of frames, for a trajectory whose frames are spread over several
  * GPUs (each rank uploads 1/N of the frames over its own PCIe link):
@@ -69,9 +73,28 @@ int psa_digitize(const float* data, const float* mean, const int32_t* idx, int64
  *     row t0, dig / expo are the full-size outputs. */
 int psa_mean_accumulate(const float* pos, int64_t n_rows, int64_t n_atoms, const float* acc_in, int64_t divide_by,
                         float* out, void* stream);
-int psa_digitize_rows(const float* data, const float* mean, const int32_t* idx, int64_t n_rows, int64_t n_atoms,
-                      int64_t n_sel, int64_t pitch, int8_t* dig, int32_t* expo, int64_t n_t_total, int64_t t0,
-                      void* stream);
+int psa_digitize_rows(const float* data, const float* mean, const float* weight, const int32_t* idx, int64_t n_rows,
+                      int64_t n_atoms, int64_t n_sel, int64_t pitch, int8_t* dig, int32_t* expo, int64_t n_t_total,
+                      int64_t t0, void* stream);
+
+/* psa_digitize_rows writing every row into SEVERAL sets of digit planes at once: this GPU's and its peers' (device
+ * pointers into other GPUs' memory obtained with psa_ipc_open).  In a multi-GPU sliced ingest each rank digitises
+ * its own frames straight into every rank's planes through NVLink - the all-gather that would follow
+ * (the one exchange step of the k-sharded path) is fused into the producing kernel.
+ *   dig_all_host / expo_all_host: HOST arrays of n_dst (<= 8) device pointers, each laid out like dig / expo above.
+ * The caller orders the ranks around the call (nobody still reads the previous planes; everybody has finished
+ * writing before anyone projects). */
+int psa_digitize_rows_peers(const float* data, const float* mean, const float* weight, const int32_t* idx, int64_t n_rows,
+                            int64_t n_atoms, int64_t n_sel, int64_t pitch, void* const* dig_all_host,
+                            void* const* expo_all_host, int64_t n_dst, int64_t n_t_total, int64_t t0, void* stream);
+
+/* CUDA IPC plumbing for the above (one process per GPU, same box):
+ *   psa_ipc_export: 64-byte handle of the allocation that contains `ptr` + the offset of `ptr` inside it (host outputs)
+ *   psa_ipc_open:   map a peer's allocation into this process (enables peer access); returns its base device pointer
+ *   psa_ipc_close:  unmap it.  An allocation may be opened once per process at a time. */
+int psa_ipc_export(const void* ptr, void* handle64_host, int64_t* offset_host);
+int psa_ipc_open(const void* handle64_host, void** base_out_host);
+int psa_ipc_close(void* base);
 
 /* Phase table exp(+i k.r) as digit planes.  theta = fma(k2,r2,fma(k1,r1,k0*r0)) in float32, then
  * correctly rounded float32 cos/sin (reference: sed_calculator.py:78, np.exp(1j*np.dot(k, r.T))).
@@ -103,11 +126,13 @@ int64_t psa_fft_workspace_bytes(int64_t n_t, int64_t n_k, int64_t n_groups);
  * in-shared-memory transform per column, other lengths through Bluestein's chirp-z identity.
  *   P   [n_groups][2 n_k][3][ldp] float32 (group g at P + g*group_stride floats)
  *   plan, workspace: see above
+ *   window [n_t] float32 or NULL: taper multiplied into every column before the transform (the README's
+ *          "window"; the shipped source has none, sed_calculator.py:83 - NULL reproduces it exactly)
  *   out coherent: complex64 [n_t][n_k_total][3], this call fills k in [k_offset, k_offset+n_k)
  *       incoherent: float32 [n_t][n_k_total] */
 int psa_fft_sed(const float* P, int64_t n_groups, int64_t group_stride, int64_t n_k, int64_t n_t,
-                int64_t ldp, const void* plan, void* workspace, int64_t workspace_bytes, int mode, void* out,
-                int64_t n_k_total, int64_t k_offset, void* stream);
+                int64_t ldp, const void* plan, void* workspace, int64_t workspace_bytes, const float* window,
+                int mode, void* out, int64_t n_k_total, int64_t k_offset, void* stream);
 
 /* Chiral phase of two complex components (reference: sed_calculator.py:338-371).
  *   z1, z2 complex64 with element strides stride1/stride2 (in complex elements), n elements
@@ -118,13 +143,29 @@ int psa_chiral_phase(const float* z1, const float* z2, int64_t n, int64_t stride
 /* intensity[r] = sum_pol |sed[r][pol]|^2 (reference: sed.py:22-24). sed complex64 [n_rows][n_pol]. */
 int psa_intensity(const float* sed, int64_t n_rows, int n_pol, float* out, void* stream);
 
-/* Inverse projection (reference: sed_calculator.py:494-499, 533):
- *   out[f][a][p] = (add_mean ? mean[a][p] : 0) + scale * Re( amp[a][p] * exp(i (2 pi f / n_frames - k_act * (mean[a] . khat))) )
- *   amp  [n_a][3][2] float64 (re, im), zero for atoms that are not reconstructed
- *   khat [3] float32 (device)          out [n_frames][n_a][3] float32
- * add_mean = 0 returns the bare oscillation (used to find max |wiggle| for the 'auto' rescale). */
-int psa_ised_frames(const float* mean, const double* amp, const float* khat, float k_act, double scale,
-                    int add_mean, int64_t n_a, int64_t n_frames, float* out, void* stream);
+/* Inverse projection, batched over (k, omega) points (reference: sed_calculator.py:440-441, 494-533).  For point p:
+ *   w[f][a][pol]   = sum over the groups g of atom a, in order, of
+ *                    Re( amp[p][g][pol] * exp(i (2 pi f / n_frames - k_act[p] * (mean[a] . khat))) )
+ *                    (float64 terms, float32 running sum like the reference's `wiggles[...] += ...`)
+ *   out[p][f][a][pol] = mean[a][pol] + (w / div[p]) * mul[p]          float32, the reference's order of operations:
+ *                    'auto' rescale: div = max |w|, mul = n-weighted std of the displacements (:517-524);
+ *                    numeric factor: div = 1, mul = factor (:527); div = mul = 1 leaves w untouched.
+ *   mean [n_a][3] float32   khat [3] float32   k_act [n_points] float32   amp [n_points][n_groups][3] complex64
+ *   member_off [n_a + 1], member_grp: CSR list of the groups each atom belongs to (ascending; empty = atom keeps
+ *   its mean position)                     out [n_points][n_frames][n_a][3] float32, n_frames <= 1024
+ * psa_ised_absmax: wmax[p] = max over frames, polarisations and the atoms of every group of |w after that group|
+ *   (the reference's running max_wiggle_amp_all, :502-504); stores nothing else. */
+int psa_ised_absmax(const float* mean, const float* khat, const float* k_act, const float* amp,
+                    const int32_t* member_off, const int32_t* member_grp, int64_t n_groups, int64_t n_a,
+                    int64_t n_frames, int64_t n_points, float* wmax, void* stream);
+int psa_ised_frames(const float* mean, const float* khat, const float* k_act, const float* amp,
+                    const int32_t* member_off, const int32_t* member_grp, int64_t n_groups, int64_t n_a,
+                    int64_t n_frames, int64_t n_points, const float* div, const float* mul, float* out, void* stream);
+
+/* out[p][0..2] = sed[w_idx[p]][k_idx[p]][0..2]: the complex amplitudes iSED reads from a group's SED
+ * (reference: sed_calculator.py:494-496).  sed complex64 [n_f][n_k][3]; out complex64 rows of out_stride elements. */
+int psa_gather_bins(const float* sed, int64_t n_k, const int32_t* w_idx, const int32_t* k_idx, int64_t n_points,
+                    int64_t out_stride, float* out, void* stream);
 
 /* sum and sum of squares of (pos - mean) over the selected atoms and all frames, float64
  * (for the 'auto' rescale of iSED, reference: sed_calculator.py:506-507).  out2 [2] float64. */
@@ -139,6 +180,12 @@ int psa_absmax(const float* x, int64_t n, float* out, void* stream);
  * full_sed_data[:, k0:k1, :] (reference: sed_calculator.py:310, 325) while the next chunk is computed. */
 int psa_copy_rows(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width, int64_t height,
                   void* stream);
+
+/* Page-lock / release caller-owned host memory so that psa_copy_rows can stream into it asynchronously.  Used for a
+ * result array in POSIX shared memory that every rank of a box maps: each rank copies its k-slice of
+ * full_sed_data[:, k0:k1] (reference: sed_calculator.py:310, 325) over its own PCIe link, no gather through rank 0. */
+int psa_host_register(void* host_ptr, int64_t bytes);
+int psa_host_unregister(void* host_ptr);
 
 #ifdef __cplusplus
 }

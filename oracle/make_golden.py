@@ -24,7 +24,7 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 
 from oracle.ref_import import load_reference  # noqa: E402
-from psa_b200 import synth  # noqa: E402
+import synthetic as synth  # noqa: E402
 
 OUT = ROOT / "tests" / "golden"
 

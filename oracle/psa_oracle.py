@@ -48,15 +48,20 @@ def phase_table(k_vecs: np.ndarray, mean_pos_group: np.ndarray) -> np.ndarray:
 
 
 def group_data(positions: np.ndarray, velocities: np.ndarray, idx: np.ndarray,
-               mean_pos: np.ndarray, use_displacements: bool) -> np.ndarray:
-    """Per-group time series that gets projected (reference: sed_calculator.py:69-72)."""
-    if use_displacements:
-        return positions[:, idx, :] - mean_pos[idx][None, :, :]
-    return velocities[:, idx, :]
+               mean_pos: np.ndarray, use_displacements: bool, weight: Optional[np.ndarray] = None) -> np.ndarray:
+    """Per-group time series that gets projected (reference: sed_calculator.py:69-72).  ``weight`` (per-atom float32,
+    e.g. sqrt(mass)) is the README-level extension the shipped source does not have: a float32 product."""
+    data = positions[:, idx, :] - mean_pos[idx][None, :, :] if use_displacements else velocities[:, idx, :]
+    if weight is not None:
+        data = (data * weight[idx].astype(F32)[None, :, None]).astype(F32)
+    return data
 
 
-def group_sed(data: np.ndarray, k_vecs: np.ndarray, mean_pos_group: np.ndarray) -> np.ndarray:
-    """Complex SED of one atom group, (n_t, n_k, 3) complex64 (reference: sed_calculator.py:58-84)."""
+def group_sed(data: np.ndarray, k_vecs: np.ndarray, mean_pos_group: np.ndarray,
+              window: Optional[np.ndarray] = None) -> np.ndarray:
+    """Complex SED of one atom group, (n_t, n_k, 3) complex64 (reference: sed_calculator.py:58-84).  ``window``
+    (float32 taper over the frames) is the README-level extension: the projected columns are multiplied by it
+    before the FFT (the shipped source has no window = None)."""
     n_t = data.shape[0]
     n_k = len(k_vecs)
     if data.shape[1] == 0:
@@ -65,14 +70,19 @@ def group_sed(data: np.ndarray, k_vecs: np.ndarray, mean_pos_group: np.ndarray) 
     proj = np.zeros((n_t, n_k, 3), C64)
     for pol in range(3):
         proj[:, :, pol] = np.einsum("ta,ak->tk", data[:, :, pol], ph.T, optimize=True)
+    if window is not None:
+        proj = proj.astype(np.complex128) * window.astype(np.float64)[:, None, None]
     return (np.fft.fft(proj, axis=0) / n_t).astype(C64)
 
 
-def group_sed_fp64(data: np.ndarray, k_vecs: np.ndarray, mean_pos_group: np.ndarray) -> np.ndarray:
+def group_sed_fp64(data: np.ndarray, k_vecs: np.ndarray, mean_pos_group: np.ndarray,
+                   window: Optional[np.ndarray] = None) -> np.ndarray:
     """Same quantity in float64, fed the reference's complex64 phase table."""
     n_t = data.shape[0]
     ph = phase_table(k_vecs, mean_pos_group).astype(np.complex128)      # float32 inputs, exact widening
     proj = np.einsum("tap,ka->tkp", data.astype(np.float64), ph, optimize=True)
+    if window is not None:
+        proj = proj * window.astype(np.float64)[:, None, None]
     return np.fft.fft(proj, axis=0) / n_t
 
 
@@ -123,7 +133,7 @@ def resolve_groups(types: np.ndarray, n_atoms: int, basis_atom_indices, basis_at
 # --------------------------------------------------------------------------- drivers
 
 def _calculate(positions, velocities, types, dt_ps, k_vecs, basis_atom_indices, basis_atom_types,
-               summation_mode, use_displacements, k_chunk_size, fp64: bool) -> Dict:
+               summation_mode, use_displacements, k_chunk_size, fp64: bool, weight=None, window=None) -> Dict:
     if summation_mode not in ("coherent", "incoherent"):
         raise ValueError(f"summation_mode must be 'coherent' or 'incoherent', got {summation_mode}")
     n_t, n_atoms = positions.shape[0], positions.shape[1]
@@ -144,35 +154,37 @@ def _calculate(positions, velocities, types, dt_ps, k_vecs, basis_atom_indices, 
             idx = np.unique(np.concatenate(groups)).astype(int) if len(groups) > 1 else groups[0]
             if idx.size == 0:
                 continue
-            data = group_data(positions, velocities, idx, mean_pos, use_displacements)
-            out[:, k0:k0 + chunk, :] = one(data, kv, mean_pos[idx])
+            data = group_data(positions, velocities, idx, mean_pos, use_displacements, weight)
+            out[:, k0:k0 + chunk, :] = one(data, kv, mean_pos[idx], window)
         else:
             acc = np.zeros((n_t, kv.shape[0]), rdt)
             for idx in groups:
                 if idx.size == 0:
                     continue
-                data = group_data(positions, velocities, idx, mean_pos, use_displacements)
-                acc += np.sum(np.abs(one(data, kv, mean_pos[idx])) ** 2, axis=-1)
+                data = group_data(positions, velocities, idx, mean_pos, use_displacements, weight)
+                acc += np.sum(np.abs(one(data, kv, mean_pos[idx], window)) ** 2, axis=-1)
             out[:, k0:k0 + chunk] = acc
     return dict(sed=out, freqs=freqs, is_complex=is_complex, mean_pos=mean_pos, groups=groups)
 
 
 def calculate(positions, velocities, types, dt_ps, k_vecs, basis_atom_indices=None,
               basis_atom_types=None, summation_mode="coherent", use_displacements=False,
-              k_chunk_size=500) -> Dict:
+              k_chunk_size=500, weight=None, window=None) -> Dict:
     """O-ref: ``SEDCalculator.calculate`` in the reference's float32 arithmetic
     (reference: sed_calculator.py:182-336).  Returns ``sed`` (complex64 (n_f,n_k,3) or float32
     (n_f,n_k)), ``freqs`` (float64, fftfreq order), ``is_complex``."""
     return _calculate(positions, velocities, types, dt_ps, k_vecs, basis_atom_indices,
-                      basis_atom_types, summation_mode, use_displacements, k_chunk_size, fp64=False)
+                      basis_atom_types, summation_mode, use_displacements, k_chunk_size, fp64=False,
+                      weight=weight, window=window)
 
 
 def calculate_fp64(positions, velocities, types, dt_ps, k_vecs, basis_atom_indices=None,
                    basis_atom_types=None, summation_mode="coherent", use_displacements=False,
-                   k_chunk_size=500) -> Dict:
+                   k_chunk_size=500, weight=None, window=None) -> Dict:
     """O-64: same driver, float64 contraction + FFT on the reference's float32 inputs."""
     return _calculate(positions, velocities, types, dt_ps, k_vecs, basis_atom_indices,
-                      basis_atom_types, summation_mode, use_displacements, k_chunk_size, fp64=True)
+                      basis_atom_types, summation_mode, use_displacements, k_chunk_size, fp64=True,
+                      weight=weight, window=window)
 
 
 def intensity(sed: np.ndarray) -> np.ndarray:

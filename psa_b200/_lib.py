@@ -22,7 +22,6 @@ MODE_COHERENT = 0
 MODE_INCOHERENT = 1
 PROJECT_TENSOR = 0
 PROJECT_SIMT = 1
-PROJECT_TENSOR_PAIR = 2
 
 LIB_PATH = Path(__file__).resolve().parent / "libpsa_b200.so"
 
@@ -32,7 +31,7 @@ _SIGNATURES = {
     "psa_device_check": (c_int, [c_int]),
     "psa_pitch": (c_int64, [c_int64]),
     "psa_mean_positions": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
-    "psa_digitize": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
+    "psa_digitize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                              c_void_p, c_void_p, c_void_p]),
     "psa_phase_digits": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                  c_void_p, c_void_p]),
@@ -42,17 +41,27 @@ _SIGNATURES = {
     "psa_fft_plan_init": (c_int, [c_int64, c_void_p, c_void_p]),
     "psa_fft_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
     "psa_fft_sed": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64,
-                            c_int, c_void_p, c_int64, c_int64, c_void_p]),
+                            c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p]),
     "psa_chiral_phase": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "psa_intensity": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
-    "psa_ised_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_double, c_int, c_int64, c_int64,
-                                c_void_p, c_void_p]),
+    "psa_ised_absmax": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                c_int64, c_void_p, c_void_p]),
+    "psa_ised_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "psa_gather_bins": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "psa_disp_moments": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "psa_absmax": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "psa_mean_accumulate": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
-    "psa_digitize_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p,
-                                  c_int64, c_int64, c_void_p]),
+    "psa_digitize_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p,
+                                  c_void_p, c_int64, c_int64, c_void_p]),
     "psa_copy_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "psa_digitize_rows_peers": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p,
+                                        c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "psa_host_register": (c_int, [c_void_p, c_int64]),
+    "psa_host_unregister": (c_int, [c_void_p]),
+    "psa_ipc_export": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "psa_ipc_open": (c_int, [c_void_p, c_void_p]),
+    "psa_ipc_close": (c_int, [c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

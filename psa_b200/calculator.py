@@ -16,6 +16,7 @@ group rules, frequency axis) is NumPy; everything O(n_t x n_atoms) runs on the G
 from __future__ import annotations
 
 import logging
+import weakref
 from pathlib import Path
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
@@ -27,26 +28,74 @@ from . import groups as grp
 from . import kspace
 from .directions import parse_direction
 from .dump import write_lammps_dump
-from .engine import K_CHUNK_CAP, DeviceTrajectory, Engine, sed_on_device
+from .engine import DeviceTrajectory, Engine, HostTarget, effective_k_chunk, sed_on_device
 from .sed import SED
 from .trajectory import Trajectory
 
 logger = logging.getLogger(__name__)
 
 _CHIRAL_AXES = {"x": (1, 2), "y": (0, 2), "z": (0, 1)}   # reference: psa_gui.py:976-982
+_ISED_BATCH_BYTES = 16 << 30                              # frames of one batched iSED launch (device memory)
+
+
+def make_window(spec, n_t: int) -> Optional[np.ndarray]:
+    """float32 taper over the frames: ``None`` (rectangular = the reference, sed_calculator.py:83), a name
+    ('hann', 'hamming', 'blackman'; periodic form, the right one for spectral estimation) or an array of n_t values."""
+    if spec is None:
+        return None
+    if isinstance(spec, str):
+        x = 2.0 * np.pi * np.arange(n_t, dtype=np.float64) / max(n_t, 1)
+        name = spec.lower()
+        if name in ("rect", "rectangular", "boxcar", "none"):
+            return None
+        if name == "hann":
+            w = 0.5 - 0.5 * np.cos(x)
+        elif name == "hamming":
+            w = 0.54 - 0.46 * np.cos(x)
+        elif name == "blackman":
+            w = 0.42 - 0.5 * np.cos(x) + 0.08 * np.cos(2.0 * x)
+        else:
+            raise ValueError(f"unknown window {spec!r} (use 'hann', 'hamming', 'blackman' or an array of n_frames values)")
+        return w.astype(np.float32)
+    w = np.asarray(spec, dtype=np.float32).reshape(-1)
+    if w.size != n_t:
+        raise ValueError(f"window has {w.size} values, the trajectory has {n_t} frames")
+    return np.ascontiguousarray(w)
+
+
+def mass_weights(masses, types: np.ndarray) -> Optional[np.ndarray]:
+    """Per-atom float32 sqrt(mass) from a per-atom array or a ``{type: mass}`` mapping (``None`` = unweighted)."""
+    if masses is None:
+        return None
+    n_atoms = len(types)
+    if isinstance(masses, dict):
+        per_atom = np.empty(n_atoms, np.float64)
+        for t in np.unique(types):
+            key = int(t)
+            if key not in masses:
+                raise ValueError(f"masses has no entry for atom type {key}")
+            per_atom[types == t] = float(masses[key])
+    else:
+        per_atom = np.asarray(masses, dtype=np.float64).reshape(-1)
+        if per_atom.size != n_atoms:
+            raise ValueError(f"masses has {per_atom.size} values, the trajectory has {n_atoms} atoms")
+    if not np.all(np.isfinite(per_atom)) or np.any(per_atom <= 0):
+        raise ValueError("masses must be positive and finite")
+    return np.sqrt(per_atom).astype(np.float32)
 
 
 class SEDCalculator:
     def __init__(self, traj: Optional[Trajectory] = None, nx: int = 1, ny: int = 1, nz: int = 1,
                  use_displacements: bool = False, dt_ps: Optional[float] = None, *,
                  positions: Optional[np.ndarray] = None, velocities: Optional[np.ndarray] = None,
-                 masses: Optional[np.ndarray] = None, types: Optional[np.ndarray] = None,
-                 lattice: Optional[np.ndarray] = None, device: Optional[int] = None):
+                 masses=None, types: Optional[np.ndarray] = None,
+                 lattice: Optional[np.ndarray] = None, device: Optional[int] = None, window=None):
+        """``masses`` (per-atom array or ``{type: mass}``) switches on the README's mass weighting: the projected
+        series becomes sqrt(m_a) v_a (float32 product).  ``window`` ('hann' | 'hamming' | 'blackman' | array of
+        n_frames values) tapers every projected column before the time FFT.  Both default to ``None`` = exactly the
+        shipped reference arithmetic, which has neither (sed_calculator.py:72, 83)."""
         if traj is None:
             traj, dt_ps = self._traj_from_arrays(positions, velocities, types, lattice, dt_ps), None
-        if masses is not None:
-            # the reference arithmetic has no mass weighting; accepted for the facade only
-            logger.info("masses are accepted for README compatibility and not used (the reference SED is unweighted).")
         if not (nx > 0 and ny > 0 and nz > 0):
             raise ValueError("System dimensions (nx, ny, nz) must be positive.")
         self.traj = traj
@@ -69,6 +118,8 @@ class SEDCalculator:
         self.b1, self.b2, self.b3 = lattice_obj.b1, lattice_obj.b2, lattice_obj.b3
         self.recip_vecs_prim = lattice_obj.recip_vecs_prim
 
+        self._weight = mass_weights(masses, np.asarray(traj.types))
+        self._window = make_window(window, traj.n_frames)
         self._device_index = device
         self._engine: Optional[Engine] = None
         self._dev_traj: Optional[DeviceTrajectory] = None
@@ -84,7 +135,7 @@ class SEDCalculator:
         return Trajectory(positions=np.asarray(positions), velocities=np.asarray(velocities),
                           types=np.asarray(types), timesteps=np.arange(len(positions)), box_matrix=box,
                           box_lengths=np.array([box[0, 0], box[1, 1], box[2, 2]], np.float32),
-                          box_tilts=np.array([box[1, 0], box[2, 0], box[2, 1]], np.float32), dt_ps=float(dt_ps))
+                          box_tilts=np.array([box[0, 1], box[0, 2], box[1, 2]], np.float32), dt_ps=float(dt_ps))
 
     @property
     def engine(self) -> Engine:
@@ -95,11 +146,13 @@ class SEDCalculator:
     @property
     def device_trajectory(self) -> DeviceTrajectory:
         if self._dev_traj is None:
-            self._dev_traj = DeviceTrajectory(self.engine, self.traj.positions, self.traj.velocities)
+            self._dev_traj = DeviceTrajectory(self.engine, self.traj.positions, self.traj.velocities,
+                                              weight=self._weight, window=self._window)
         return self._dev_traj
 
     def release_device_memory(self) -> None:
-        """Drop every device buffer (the next call re-uploads the trajectory)."""
+        """Drop every device buffer (the next call re-uploads the trajectory).  Call this after modifying the
+        trajectory's arrays in place: uploads, mean positions and digit planes are cached per calculator."""
         self._dev_traj = None
 
     # ------------------------------------------------------------------ k-space (host)
@@ -141,11 +194,11 @@ class SEDCalculator:
         k_chunk = max(1, int(k_chunk_size))
         n_t, n_k = self.traj.n_frames, k_vecs.shape[0]
         with torch.cuda.device(self.engine.device):
-            if to_host and n_k > min(k_chunk, K_CHUNK_CAP):
+            if to_host and n_k > effective_k_chunk(k_chunk, n_k):
                 host = torch.empty((n_t, n_k, 3) if complex_out else (n_t, n_k),
                                    dtype=torch.complex64 if complex_out else torch.float32, pin_memory=True)
                 sed_on_device(self.device_trajectory, k_vecs, proj_groups, complex_out, self.use_displacements,
-                              k_chunk=k_chunk, host_out=host)
+                              k_chunk=k_chunk, host_out=HostTarget(host.data_ptr(), n_k, 0, n_t, host))
                 self.engine.copy_stream.synchronize()
                 return host.numpy(), complex_out, groups
             out = sed_on_device(self.device_trajectory, k_vecs, proj_groups, complex_out,
@@ -176,10 +229,10 @@ class SEDCalculator:
         k_vecs = np.ascontiguousarray(np.asarray(k_vectors_3d, dtype=np.float32).reshape(-1, 3))
         k_chunk, n_k = max(1, int(k_chunk_size)), k_vecs.shape[0]
         with torch.cuda.device(self.engine.device):
-            if n_k > min(k_chunk, K_CHUNK_CAP):
+            if n_k > effective_k_chunk(k_chunk, n_k):
                 host = torch.empty((n_rows, n_k), dtype=torch.float32, pin_memory=True)
                 sed_on_device(self.device_trajectory, k_vecs, proj_groups, False, self.use_displacements,
-                              k_chunk=k_chunk, host_out=host, n_rows=n_rows)
+                              k_chunk=k_chunk, host_out=HostTarget(host.data_ptr(), n_k, 0, n_rows, host))
                 self.engine.copy_stream.synchronize()
                 inten = host.numpy()
             else:
@@ -196,7 +249,9 @@ class SEDCalculator:
         return host.numpy()
 
     def _context(self, groups: List[np.ndarray]) -> Dict:
-        return dict(calculator=self, groups=groups, types=self.traj.types, box_matrix=self.traj.box_matrix)
+        """What ``iSEDReconstructor(result)`` needs: geometry plus a WEAK reference to this calculator (a result must
+        not keep the trajectory's device buffers alive, and stays picklable - ``SED.__getstate__`` drops the reference)."""
+        return dict(calculator=weakref.ref(self), groups=groups, types=self.traj.types, box_matrix=self.traj.box_matrix)
 
     # ------------------------------------------------------------------ chirality
     def calculate_chiral_phase(self, Z1: np.ndarray, Z2: np.ndarray, angle_range_opt: str = "C") -> np.ndarray:
@@ -285,75 +340,88 @@ class SEDCalculator:
 
         eng, dtraj = self.engine, self.device_trajectory
         results: List[Dict] = []
+        n_pts, n_grp, n_fr = len(targets), len(recon_groups), int(n_recon_frames)
+        if n_pts == 0:
+            return results
+        # groups of every atom as a CSR list, in the reference's group-loop order; a group counts once per atom
+        # (the reference's fancy-indexed `+=` ignores duplicate indices, sed_calculator.py:499)
+        members = [np.unique(g) for g in recon_groups]
+        counts = np.zeros(n_atoms + 1, np.int64)
+        for m in members:
+            counts[m + 1] += 1
+        member_off = np.cumsum(counts)
+        member_grp = np.zeros(max(1, int(member_off[-1])), np.int32)
+        fill = member_off[:-1].copy()
+        for gi, m in enumerate(members):
+            member_grp[fill[m]] = gi
+            fill[m] += 1
         with torch.cuda.device(eng.device):
-            # amplitudes S_g[w, k, pol] for every group at the matched points only
-            w_sel = torch.tensor(w_idx, device=eng.device)
-            c_sel = torch.tensor([col_of[k] for k in k_idx], device=eng.device)
-            amps = []
-            for g in recon_groups:
+            # amplitudes S_g[w, k, pol] of every group at the matched bins only
+            w_dev = eng.upload_small(np.asarray(w_idx, np.int32))
+            c_dev = eng.upload_small(np.asarray([col_of[k] for k in k_idx], np.int32))
+            amp = eng.empty((n_pts, n_grp, 3), torch.complex64)
+            for gi, g in enumerate(recon_groups):
                 sed_g = sed_on_device(dtraj, k_vecs[uniq_k], [g], True, self.use_displacements)
-                amps.append(sed_g[w_sel, c_sel, :].cpu().numpy())            # (n_targets, 3) complex64
+                eng._run("psa_gather_bins", 1, sed_g.data_ptr(), len(uniq_k), w_dev.data_ptr(), c_dev.data_ptr(), n_pts,
+                         n_grp * 3, amp.data_ptr() + gi * 3 * 8, eng.stream())
+                del sed_g
             mean = dtraj.mean
-            khat_dev = torch.from_numpy(np.ascontiguousarray(k_hat, np.float32)).to(eng.device)
-            std_scale = 0.0
-            if auto:                                                           # reference: sed_calculator.py:502-508
+            khat_dev = eng.upload_small(np.ascontiguousarray(k_hat, np.float32))
+            kact = np.asarray([k_mags[k] for k in k_idx], np.float32)
+            kact_dev = eng.upload_small(kact)
+            off_dev = eng.upload_small(member_off.astype(np.int32))
+            grp_dev = eng.upload_small(member_grp)
+            batch_args = (mean.data_ptr(), khat_dev.data_ptr())
+
+            div, mul = np.ones(n_pts, np.float32), np.ones(n_pts, np.float32)
+            if auto:                                                           # reference: sed_calculator.py:502-524
                 num, den = 0.0, 0
                 mom = eng.empty((2,), torch.float64)
                 for g in recon_groups:
-                    idx_dev = torch.from_numpy(np.ascontiguousarray(g, np.int32)).to(eng.device)
-                    _lib.call("psa_disp_moments", dtraj.positions.data_ptr(), mean.data_ptr(), idx_dev.data_ptr(),
-                              traj.n_frames, n_atoms, int(g.size), mom.data_ptr(), eng.stream())
+                    idx_dev = eng.upload_small(np.ascontiguousarray(g, np.int32))
+                    eng._run("psa_disp_moments", 1, dtraj.positions.data_ptr(), mean.data_ptr(), idx_dev.data_ptr(),
+                             traj.n_frames, n_atoms, int(g.size), mom.data_ptr(), eng.stream())
                     s1, s2 = mom.cpu().tolist()
                     n_el = traj.n_frames * int(g.size) * 3
                     var = max(s2 / n_el - (s1 / n_el) ** 2, 0.0)
                     num += float(np.sqrt(var)) * int(g.size)
                     den += int(g.size)
                 std_scale = num / den if den > 0 else 0.0
+                wmax = eng.empty((n_pts,), torch.float32)
+                eng._run("psa_ised_absmax", 1, *batch_args, kact_dev.data_ptr(), amp.data_ptr(), off_dev.data_ptr(),
+                         grp_dev.data_ptr(), n_grp, n_atoms, n_fr, n_pts, wmax.data_ptr(), eng.stream())
+                wmax_host = self._to_host(wmax)
+                for p in range(n_pts):
+                    if wmax_host[p] > 1e-9:
+                        div[p] = wmax_host[p]
+                        if std_scale > 1e-9:
+                            mul[p] = np.float32(std_scale)
+                    else:
+                        logger.warning("iSED: Max wiggle amp near zero. Auto-rescaling ineffective.")
+            elif isinstance(rescale_factor, (int, float)):
+                mul[:] = np.float32(rescale_factor)
+            div_dev, mul_dev = eng.upload_small(div), eng.upload_small(mul)
 
-            # per-atom amplitudes of every target at once: (n_targets, n_atoms, 3) complex128, uploaded in batches
-            members = [np.unique(g) for g in recon_groups]                     # the reference adds a group once per atom
-            batch = max(1, (256 << 20) // (n_atoms * 48))
-            for t0 in range(0, len(targets), batch):
-                t1 = min(len(targets), t0 + batch)
-                amp_all = np.zeros((t1 - t0, n_atoms, 3), np.complex128)
-                for m, a in zip(members, amps):
-                    amp_all[:, m, :] += a[t0:t1].astype(np.complex128)[:, None, :]
-                amp_dev_all = torch.from_numpy(amp_all.view(np.float64).reshape(t1 - t0, n_atoms, 3, 2)).to(eng.device)
-                for ti in range(t0, t1):
+            per_point = n_fr * n_atoms * 12
+            batch = max(1, min(n_pts, _ISED_BATCH_BYTES // max(per_point, 1)))
+            for p0 in range(0, n_pts, batch):
+                p1 = min(n_pts, p0 + batch)
+                frames = eng.empty((p1 - p0, n_fr, n_atoms, 3), torch.float32)
+                eng._run("psa_ised_frames", 1, *batch_args, kact_dev.data_ptr() + 4 * p0,
+                         amp.data_ptr() + p0 * n_grp * 3 * 8, off_dev.data_ptr(), grp_dev.data_ptr(), n_grp, n_atoms, n_fr,
+                         p1 - p0, div_dev.data_ptr() + 4 * p0, mul_dev.data_ptr() + 4 * p0, frames.data_ptr(), eng.stream())
+                if keep_on_device:
+                    host_frames = frames
+                elif n_pts == 1:
+                    host_frames = self._to_host(frames)
+                else:       # many frame sets: one plain host array (a pinned buffer of this size costs more than the copy)
+                    host_frames = np.empty(tuple(frames.shape), np.float32)
+                    torch.from_numpy(host_frames).copy_(frames)
+                for ti in range(p0, p1):
                     kt, wt = targets[ti]
-                    amp_dev = amp_dev_all[ti - t0]
-                    k_act = float(k_mags[k_idx[ti]])
-                    frames = eng.empty((n_recon_frames, n_atoms, 3), torch.float32)
-                    scale = 1.0
-                    if auto:
-                        self._ised_kernel(mean, amp_dev, khat_dev, k_act, 1.0, 0, n_atoms, n_recon_frames, frames)
-                        mx = eng.empty((1,), torch.float32)
-                        _lib.call("psa_absmax", frames.data_ptr(), frames.numel(), mx.data_ptr(), eng.stream())
-                        max_amp = float(mx.item())
-                        if max_amp > 1e-9:
-                            scale = 1.0 / max_amp
-                            if std_scale > 1e-9:
-                                scale *= std_scale
-                        else:
-                            logger.warning("iSED: Max wiggle amp near zero. Auto-rescaling ineffective.")
-                    elif isinstance(rescale_factor, (int, float)):
-                        scale = float(rescale_factor)
-                    self._ised_kernel(mean, amp_dev, khat_dev, k_act, scale, 1, n_atoms, n_recon_frames, frames)
-                    if keep_on_device:
-                        host = frames
-                    elif len(targets) == 1:
-                        host = self._to_host(frames)
-                    else:                       # many frame sets: plain host arrays (a pinned buffer per set costs more than the copy)
-                        host = np.empty(tuple(frames.shape), np.float32)
-                        torch.from_numpy(host).copy_(frames)
-                    results.append(dict(frames=host, k_index=k_idx[ti], w_index=w_idx[ti], k_actual=k_act,
-                                        w_actual=float(freqs[w_idx[ti]]), k_target=kt, w_target=wt))
+                    results.append(dict(frames=host_frames[ti - p0], k_index=k_idx[ti], w_index=w_idx[ti],
+                                        k_actual=float(kact[ti]), w_actual=float(freqs[w_idx[ti]]), k_target=kt, w_target=wt))
         return results
-
-    def _ised_kernel(self, mean, amp_dev, khat_dev, k_act, scale, add_mean, n_atoms, n_frames, out) -> None:
-        _lib.call("psa_ised_frames", mean.data_ptr(), amp_dev.data_ptr(), khat_dev.data_ptr(), float(k_act),
-                  float(scale), int(add_mean), n_atoms, n_frames, out.data_ptr(), self.engine.stream())
-        self.engine.launches += 1
 
     def ised(self, k_dir_spec, k_target: float, w_target: float, char_len_k_path: float, nk_on_path: int = 100,
              bz_cov_ised: float = 1.0, basis_atom_idx_ised: Optional[List[int]] = None,
@@ -385,7 +453,10 @@ class iSEDReconstructor:
             raise ValueError("iSEDReconstructor needs a result produced by psa_b200.SEDCalculator "
                              "(it carries the trajectory geometry).")
         self._sed = sed_result
-        self._calc: SEDCalculator = ctx["calculator"]
+        calc = ctx["calculator"]
+        self._calc: SEDCalculator = calc() if isinstance(calc, weakref.ref) else calc
+        if self._calc is None:
+            raise ValueError("the SEDCalculator that produced this result no longer exists (iSED needs its trajectory)")
         self._k_hat = ctx.get("k_hat")
         if self._k_hat is None:
             vecs = np.asarray(sed_result.k_vectors, dtype=np.float32)

@@ -522,27 +522,43 @@ __device__ void transform_and_emit(sc* __restrict__ s, const FftGeom& g, int r, 
 // ---------------------------------------------------------------------------------------------
 // fetchers (return the element widened to float64)
 // ---------------------------------------------------------------------------------------------
-struct FetchPlanar {            // rows of P: Re and Im as separate float rows
+struct FetchPlanar {            // rows of P: Re and Im as separate float rows; optional taper (exact in float64)
   const float* re;
   const float* im;
-  __device__ cd operator()(int t) const { return mk((double)__ldg(re + t), (double)__ldg(im + t)); }
+  const float* win;
+  __device__ cd operator()(int t) const {
+    cd v = mk((double)__ldg(re + t), (double)__ldg(im + t));
+    if (win != nullptr) {
+      const double w = (double)__ldg(win + t);
+      v.x *= w;
+      v.y *= w;
+    }
+    return v;
+  }
 };
 struct FetchChirped {           // x_t * conj(b_t) for t < n, zero padding up to the transform length
   const float* re;
   const float* im;
+  const float* win;
   const double2* chirp;
   int n;
   __device__ cd operator()(int t) const {
     if (t >= n) return mk(0.0, 0.0);
     const double2 b = __ldg(chirp + t);
-    return cmul_conj(mk((double)__ldg(re + t), (double)__ldg(im + t)), mk(b.x, b.y));
+    cd v = mk((double)__ldg(re + t), (double)__ldg(im + t));
+    if (win != nullptr) {
+      const double w = (double)__ldg(win + t);
+      v.x *= w;
+      v.y *= w;
+    }
+    return cmul_conj(v, mk(b.x, b.y));
   }
 };
-struct FetchConj {              // conj of an interleaved complex column (inverse transform by conjugation)
-  const float2* src;
+struct FetchConj {              // conj of an interleaved complex128 column (inverse transform by conjugation)
+  const double2* src;
   __device__ cd operator()(int t) const {
-    float2 v = __ldg(src + t);
-    return mk((double)v.x, -(double)v.y);
+    double2 v = __ldg(src + t);
+    return mk(v.x, -v.y);
   }
 };
 struct FetchComplexD {
@@ -596,12 +612,13 @@ struct SinkAccumulate {         // s_acc[slot] += |S|^2 of the float32 S; the sl
     if (post(f, v, S)) s_acc[slot] += S.x * S.x + S.y * S.y;
   }
 };
-struct SinkTimesSpectrum {      // natural-order float32 store of value * bhat[f] (Bluestein forward leg)
-  float2* dst;
+struct SinkTimesSpectrum {      // natural-order float64 store of value * bhat[f] (Bluestein forward leg; the chirped
+  double2* dst;                 // spectrum stays in float64 between the two legs - one float32 rounding in total)
   const double2* bhat;
   __device__ void operator()(int, int f, cd v) const {
     const double2 b = __ldg(bhat + f);
-    dst[f] = narrow(cmul(v, mk(b.x, b.y)));
+    const cd y = cmul(v, mk(b.x, b.y));
+    dst[f] = make_double2(y.x, y.y);
   }
 };
 struct SinkStoreD {             // natural-order float64 store (plan construction)
@@ -620,6 +637,7 @@ struct SedArgs {
   void* out;
   int64_t n_k_total, k_offset;
   double inv_n_t;           // 1 / n_t from the host: a float64 division per CTA showed up as 5 % of the stall samples
+  const float* window;      // optional taper w[t] (NULL = rectangular, the reference)
 };
 
 __device__ __forceinline__ void column_rows(const SedArgs& a, int g, int k, int pol, const float*& re, const float*& im) {
@@ -658,6 +676,7 @@ __global__ void __launch_bounds__(kFftThreads, kFftMinCtas) fft_sed_kernel(SedAr
   if (kMode == PSA_MODE_COHERENT) {          // block -> (k, pol, r)
     const int pol = (blockIdx.x / g.R) % 3, k = blockIdx.x / (3 * g.R);
     FetchPlanar fetch;
+    fetch.win = a.window;
     column_rows(a, 0, k, pol, fetch.re, fetch.im);
     load_column(s_data, fetch, g, r);
     __syncthreads();
@@ -672,6 +691,7 @@ __global__ void __launch_bounds__(kFftThreads, kFftMinCtas) fft_sed_kernel(SedAr
     for (int grp = 0; grp < a.n_groups; ++grp)
       for (int pol = 0; pol < 3; ++pol) {
         FetchPlanar fetch;
+        fetch.win = a.window;
         column_rows(a, grp, k, pol, fetch.re, fetch.im);
         __syncthreads();
         load_column(s_data, fetch, g, r);
@@ -720,6 +740,7 @@ __global__ void __launch_bounds__(kFftThreads, kFftMinCtas) fft_sed_cluster_kern
   const int col0 = (blockIdx.x / (C * g.R)) * C, col = col0 + rank;
   if (col < n_cols) {
     FetchPlanar fetch;
+    fetch.win = a.window;
     column_rows(a, 0, col / 3, col % 3, fetch.re, fetch.im);
     load_column(s_data, fetch, g, r);
     __syncthreads();
@@ -755,12 +776,13 @@ __global__ void __launch_bounds__(kFftThreads, kFftMinCtas) fft_sed_cluster_kern
 __global__ void __launch_bounds__(kFftThreads, kFftMinCtas) bluestein_forward_kernel(SedArgs a, FftGeom g, int n_k,
                                                                         const double2* __restrict__ chirp,
                                                                         const double2* __restrict__ bhat,
-                                                                        float2* __restrict__ scratch) {
+                                                                        double2* __restrict__ scratch) {
   extern __shared__ sc s_data[];
   const int r = blockIdx.x % g.R;
   const int col = blockIdx.x / g.R;
   const int pol = col % 3, k = (col / 3) % n_k, grp = col / (3 * n_k);
   FetchChirped fetch;
+  fetch.win = a.window;
   column_rows(a, grp, k, pol, fetch.re, fetch.im);
   fetch.chirp = chirp;
   fetch.n = a.n_t;
@@ -774,7 +796,7 @@ __global__ void __launch_bounds__(kFftThreads, kFftMinCtas) bluestein_forward_ke
 template <int kMode>
 __global__ void __launch_bounds__(kFftThreads, kFftMinCtas) bluestein_inverse_kernel(SedArgs a, FftGeom g, int n_k,
                                                                         const double2* __restrict__ chirp,
-                                                                        const float2* __restrict__ scratch) {
+                                                                        const double2* __restrict__ scratch) {
   extern __shared__ sc s_data[];
   const Unchirp post{chirp, a.n_t, 1.0 / (double)g.n_fft, (double)a.n_t};
   const int r = blockIdx.x % g.R;
@@ -917,8 +939,8 @@ static int build_tables(int64_t n_fft, double2* tw, cudaStream_t s) {
 }
 
 int fft_plan_bytes(int64_t n_t, int64_t* bytes) {
-  if (n_t < 2 || n_t > kMaxTransform / 2) {
-    set_error("psa_fft: n_t=%lld is outside the supported range [2, %lld]", (long long)n_t, (long long)(kMaxTransform / 2));
+  if (n_t < 1 || n_t > kMaxTransform / 2) {
+    set_error("psa_fft: n_t=%lld is outside the supported range [1, %lld]", (long long)n_t, (long long)(kMaxTransform / 2));
     return PSA_ERR_UNSUPPORTED;
   }
   if (direct_length(n_t)) {
@@ -954,13 +976,13 @@ int fft_workspace_bytes(int64_t n_t, int64_t n_k, int64_t n_groups, int64_t* byt
   int64_t plan = 0;
   int st = fft_plan_bytes(n_t, &plan);
   if (st != PSA_OK) return st;
-  *bytes = direct_length(n_t) ? 0 : n_groups * n_k * 3 * bluestein_length(n_t) * (int64_t)sizeof(float2);
+  *bytes = direct_length(n_t) ? 0 : n_groups * n_k * 3 * bluestein_length(n_t) * (int64_t)sizeof(double2);
   return PSA_OK;
 }
 
 int launch_fft(const float* P, int64_t n_groups, int64_t group_stride, int64_t n_k, int64_t n_t, int64_t ldp,
-               const void* plan_buf, void* workspace, int64_t workspace_bytes, int mode, void* out, int64_t n_k_total,
-               int64_t k_offset, cudaStream_t s) {
+               const void* plan_buf, void* workspace, int64_t workspace_bytes, const float* window, int mode, void* out,
+               int64_t n_k_total, int64_t k_offset, cudaStream_t s) {
   if (n_k == 0 || n_t == 0) return PSA_OK;
   PSA_REQUIRE(mode == PSA_MODE_COHERENT || mode == PSA_MODE_INCOHERENT, "psa_fft_sed: unknown mode %d", mode);
   int64_t need = 0;
@@ -970,7 +992,7 @@ int launch_fft(const float* P, int64_t n_groups, int64_t group_stride, int64_t n
               "psa_fft_sed: workspace of %lld bytes required for n_t=%lld (got %lld)", (long long)need,
               (long long)n_t, (long long)workspace_bytes);
   const double2* plan = reinterpret_cast<const double2*>(plan_buf);
-  SedArgs a{P, (int)n_groups, group_stride, ldp, (int)n_t, out, n_k_total, k_offset, 1.0 / (double)n_t};
+  SedArgs a{P, (int)n_groups, group_stride, ldp, (int)n_t, out, n_k_total, k_offset, 1.0 / (double)n_t, window};
   const bool coherent = mode == PSA_MODE_COHERENT;
 
   if (need == 0) {                                       // power of two: one fused kernel
@@ -1009,7 +1031,7 @@ int launch_fft(const float* P, int64_t n_groups, int64_t group_stride, int64_t n
   const double2* tw = plan;
   const double2* chirp = tw + M + pass_table_entries(M);
   const double2* bhat = chirp + n_t;
-  float2* scratch = reinterpret_cast<float2*>(workspace);
+  double2* scratch = reinterpret_cast<double2*>(workspace);
   FftGeom g = make_geom(M, tw);
   if ((st = allow_smem(bluestein_forward_kernel, smem_bytes(g, false))) != PSA_OK) return st;
   bluestein_forward_kernel<<<(unsigned)(n_groups * n_k * 3 * g.R), kFftThreads, smem_bytes(g, false), s>>>(

@@ -201,6 +201,7 @@ int launch_mean_accumulate(const float* pos, int64_t n_t, int64_t n_a, const flo
                            cudaStream_t s) {
   int64_t n_cols = n_a * 3;
   if (n_cols == 0) return PSA_OK;
+  DeviceGuard guard(mean);
   const float divisor = divide_by > 0 ? (float)divide_by : 0.f;
   if (n_t > 0 && mean_use_tma(pos, n_t, n_cols)) {
     CUtensorMap map;
@@ -241,9 +242,12 @@ int launch_mean_accumulate(const float* pos, int64_t n_t, int64_t n_a, const flo
 template <bool kStaged>
 __device__ __forceinline__ float row_value(const float* p) { return kStaged ? *p : __ldg(p); }
 
+// `weight` (or NULL): one float32 factor per atom, applied after the mean subtraction - the README facade's
+// mass weighting sqrt(m) v (reference: README.md:83-101; the shipped source is unweighted, weight == NULL).
 template <bool kStaged>
 __device__ __forceinline__ void load_quad(const float* __restrict__ row, const float* __restrict__ mean,
-                                          const int32_t* __restrict__ idx, int64_t j0, int64_t n_sel, float (&v)[12]) {
+                                          const float* __restrict__ weight, const int32_t* __restrict__ idx, int64_t j0,
+                                          int64_t n_sel, float (&v)[12]) {
   const float* src = row + j0 * 3;
   if (idx == nullptr && j0 + 4 <= n_sel && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
     const float4* s4 = reinterpret_cast<const float4*>(src);
@@ -257,6 +261,14 @@ __device__ __forceinline__ void load_quad(const float* __restrict__ row, const f
 #pragma unroll
       for (int i = 0; i < 12; ++i) v[i] = __fsub_rn(v[i], __ldg(m + i));
     }
+    if (weight != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float w = __ldg(weight + j0 + q);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[q * 3 + c] = __fmul_rn(v[q * 3 + c], w);
+      }
+    }
     return;
   }
 #pragma unroll
@@ -268,6 +280,7 @@ __device__ __forceinline__ void load_quad(const float* __restrict__ row, const f
       for (int p = 0; p < 3; ++p) {
         float x = row_value<kStaged>(row + atom * 3 + p);
         if (mean != nullptr) x = __fsub_rn(x, __ldg(mean + atom * 3 + p));
+        if (weight != nullptr) x = __fmul_rn(x, __ldg(weight + atom));
         v[q * 3 + p] = x;
       }
     } else {
@@ -276,14 +289,26 @@ __device__ __forceinline__ void load_quad(const float* __restrict__ row, const f
   }
 }
 
-// exponent e with m < 2^e (kExpMin for an all-zero or non-finite row)
-__device__ __forceinline__ int row_exponent(float m) {
+// Row maxima are tracked as the bit pattern of |x| (an unsigned integer max orders finite floats like fmaxf does,
+// and - unlike fmaxf, which drops NaN - lets NaN and Inf win, so that a corrupt frame cannot pass silently).
+__device__ __forceinline__ uint32_t abs_bits(float x) { return __float_as_uint(x) & 0x7fffffffu; }
+
+// exponent e with m < 2^e (kExpMin for an all-zero row); kExpPoison when the row holds a NaN, an infinity or a value
+// >= 2^kExpMax: the reference propagates those into the spectrum (sed_calculator.py:81-84), and so does the
+// projection epilogue for a poisoned row.
+__device__ __forceinline__ int row_exponent(uint32_t m_bits) {
+  if (m_bits >= 0x7f800000u) return kExpPoison;
+  const float m = __uint_as_float(m_bits);
   int e = kExpMin;
-  if (m > 0.f && isfinite(m)) {
+  if (m > 0.f) {
     frexpf(m, &e);                         // m = f * 2^e with f in [0.5,1)  =>  m < 2^e
-    e = max(kExpMin, min(kExpMax, e));
+    if (e > kExpMax) return kExpPoison;
+    e = max(kExpMin, e);
   }
   return e;
+}
+__device__ __forceinline__ float row_scale(int e) {      // 2^(30 - e), exact; a poisoned row digitises as zeros
+  return e == kExpPoison ? 0.f : exp2f((float)(kFracBits - e));
 }
 
 // Digit-plane words of four atoms.  Digits without a carry chain: with Y = X + 0x00808080 the low three bytes
@@ -312,14 +337,14 @@ __device__ __forceinline__ void quad_words(const float (&v)[12], const float (&s
 template <bool kStaged>
 __global__ void __launch_bounds__(512) digitize_kernel(const float* __restrict__ data,
                                                        const float* __restrict__ mean,
+                                                       const float* __restrict__ weight,
                                                        const int32_t* __restrict__ idx, int64_t n_t,
                                                        int64_t n_a, int64_t n_sel, int64_t pitch,
-                                                       int8_t* __restrict__ dig, int32_t* __restrict__ expo,
-                                                       int64_t t0) {
+                                                       DigDests dst, int64_t t0) {
   // `data` holds the rows [t0, t0 + gridDim.x) of a trajectory of n_t frames; dig / expo describe all n_t frames
   const int64_t t = t0 + blockIdx.x;
   const float* row = data + (int64_t)blockIdx.x * n_a * 3;
-  __shared__ float s_max[3][32];
+  __shared__ uint32_t s_max[3][32];
   __shared__ int s_exp[3];
   if (kStaged) {
     extern __shared__ __align__(128) float s_row[];
@@ -339,13 +364,13 @@ __global__ void __launch_bounds__(512) digitize_kernel(const float* __restrict__
     row = s_row;
   }
 
-  float mx[3] = {0.f, 0.f, 0.f};
+  uint32_t mx[3] = {0u, 0u, 0u};
   if (idx == nullptr) {
     for (int64_t j0 = (int64_t)threadIdx.x * 4; j0 < n_sel; j0 += (int64_t)blockDim.x * 4) {
       float v[12];
-      load_quad<kStaged>(row, mean, idx, j0, n_sel, v);
+      load_quad<kStaged>(row, mean, weight, idx, j0, n_sel, v);
 #pragma unroll
-      for (int i = 0; i < 12; ++i) mx[i % 3] = fmaxf(mx[i % 3], fabsf(v[i]));
+      for (int i = 0; i < 12; ++i) mx[i % 3] = max(mx[i % 3], abs_bits(v[i]));
     }
   } else {   // gather: one selected atom per thread keeps neighbouring lanes on neighbouring atoms
     for (int64_t j = threadIdx.x; j < n_sel; j += blockDim.x) {
@@ -354,43 +379,49 @@ __global__ void __launch_bounds__(512) digitize_kernel(const float* __restrict__
       for (int p = 0; p < 3; ++p) {
         float x = row_value<kStaged>(row + atom * 3 + p);
         if (mean != nullptr) x = __fsub_rn(x, __ldg(mean + atom * 3 + p));
-        mx[p] = fmaxf(mx[p], fabsf(x));
+        if (weight != nullptr) x = __fmul_rn(x, __ldg(weight + atom));
+        mx[p] = max(mx[p], abs_bits(x));
       }
     }
   }
 #pragma unroll
   for (int p = 0; p < 3; ++p) {
-    float m = mx[p];
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    uint32_t m = mx[p];
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) s_max[p][threadIdx.x >> 5] = m;
   }
   __syncthreads();
   if (threadIdx.x < 3) {
-    float m = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s_max[threadIdx.x][w]);
+    uint32_t m = 0u;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = max(m, s_max[threadIdx.x][w]);
     const int e = row_exponent(m);
     s_exp[threadIdx.x] = e;
-    expo[threadIdx.x * n_t + t] = e;
+    for (int d = 0; d < dst.n; ++d) dst.expo[d][threadIdx.x * n_t + t] = e;
   }
   __syncthreads();
 
   float scale[3];
 #pragma unroll
-  for (int p = 0; p < 3; ++p) scale[p] = exp2f((float)(kFracBits - s_exp[p]));   // exact power of two
+  for (int p = 0; p < 3; ++p) scale[p] = row_scale(s_exp[p]);   // exact power of two
 
   const int64_t plane = n_t * pitch;                 // bytes of one (pol, slice) plane
   for (int64_t j0 = (int64_t)threadIdx.x * 4; j0 < pitch; j0 += (int64_t)blockDim.x * 4) {
     uint32_t word[3][kSlices] = {};
     if (j0 < n_sel) {
       float v[12];
-      load_quad<kStaged>(row, mean, idx, j0, n_sel, v);      // entries past n_sel come back as zeros -> zero digits
+      load_quad<kStaged>(row, mean, weight, idx, j0, n_sel, v);      // entries past n_sel come back as zeros -> zero digits
       quad_words(v, scale, word);
     }
+    // every destination gets the row: this GPU's planes and, in a multi-GPU sliced ingest, the peers' planes through
+    // NVLink (a warp stores 128 contiguous bytes per plane: one full-size NVLink write each)
+    for (int d = 0; d < dst.n; ++d) {
+      int8_t* dig = dst.dig[d];
 #pragma unroll
-    for (int p = 0; p < 3; ++p)
+      for (int p = 0; p < 3; ++p)
 #pragma unroll
-      for (int sl = 0; sl < kSlices; ++sl)
-        *reinterpret_cast<uint32_t*>(dig + (int64_t)(p * kSlices + sl) * plane + t * pitch + j0) = word[p][sl];
+        for (int sl = 0; sl < kSlices; ++sl)
+          *reinterpret_cast<uint32_t*>(dig + (int64_t)(p * kSlices + sl) * plane + t * pitch + j0) = word[p][sl];
+    }
   }
 }
 
@@ -400,12 +431,12 @@ __global__ void __launch_bounds__(512) digitize_kernel(const float* __restrict__
 // and keeps it in shared memory, the per-polarisation maxima are exchanged through distributed shared memory,
 // and the digits are produced from the staged copy - the frame is read from HBM exactly once.
 __global__ void __launch_bounds__(256)
-digitize_cluster_kernel(const float* __restrict__ data, const float* __restrict__ mean, int64_t n_t, int64_t n_a,
-                        int64_t pitch, int slice_atoms, int8_t* __restrict__ dig, int32_t* __restrict__ expo,
-                        int64_t t0) {
+digitize_cluster_kernel(const float* __restrict__ data, const float* __restrict__ mean,
+                        const float* __restrict__ weight, int64_t n_t, int64_t n_a,
+                        int64_t pitch, int slice_atoms, DigDests dst, int64_t t0) {
   extern __shared__ __align__(128) float s_row[];     // this CTA's slice of the frame
   __shared__ uint64_t row_bar;
-  __shared__ float s_max[3][8], s_loc[3];
+  __shared__ uint32_t s_max[3][8], s_loc[3];
   uint32_t rank, kDigCluster;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(kDigCluster));
@@ -425,41 +456,42 @@ digitize_cluster_kernel(const float* __restrict__ data, const float* __restrict_
   __syncthreads();
   mbar_wait(&row_bar, 0);
   const float* lmean = mean != nullptr ? mean + a0 * 3 : nullptr;
+  const float* lweight = weight != nullptr ? weight + a0 : nullptr;
 
-  float mx[3] = {0.f, 0.f, 0.f};
+  uint32_t mx[3] = {0u, 0u, 0u};
   for (int j0 = threadIdx.x * 4; j0 < n_loc; j0 += blockDim.x * 4) {
     float v[12];
-    load_quad<true>(s_row, lmean, nullptr, j0, n_loc, v);
+    load_quad<true>(s_row, lmean, lweight, nullptr, j0, n_loc, v);
 #pragma unroll
-    for (int i = 0; i < 12; ++i) mx[i % 3] = fmaxf(mx[i % 3], fabsf(v[i]));
+    for (int i = 0; i < 12; ++i) mx[i % 3] = max(mx[i % 3], abs_bits(v[i]));
   }
 #pragma unroll
   for (int p = 0; p < 3; ++p) {
-    float m = mx[p];
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    uint32_t m = mx[p];
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) s_max[p][threadIdx.x >> 5] = m;
   }
   __syncthreads();
   if (threadIdx.x < 3) {
-    float m = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s_max[threadIdx.x][w]);
+    uint32_t m = 0u;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = max(m, s_max[threadIdx.x][w]);
     s_loc[threadIdx.x] = m;
   }
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   float scale[3];
 #pragma unroll
   for (int p = 0; p < 3; ++p) {                        // every thread folds the CTAs' maxima (3 x cluster size remote reads)
-    float m = 0.f;
+    uint32_t m = 0u;
     for (uint32_t c = 0; c < kDigCluster; ++c) {
-      uint32_t remote;
-      float val;
+      uint32_t remote, val;
       asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_addr(&s_loc[p])), "r"(c));
-      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(val) : "r"(remote) : "memory");
-      m = fmaxf(m, val);
+      asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(val) : "r"(remote) : "memory");
+      m = max(m, val);
     }
     const int e = row_exponent(m);
-    if (rank == 0 && threadIdx.x == 0) expo[p * n_t + t] = e;
-    scale[p] = exp2f((float)(kFracBits - e));
+    if (rank == 0 && threadIdx.x == 0)
+      for (int d = 0; d < dst.n; ++d) dst.expo[d][p * n_t + t] = e;
+    scale[p] = row_scale(e);
   }
 
   const int64_t plane = n_t * pitch;
@@ -469,35 +501,43 @@ digitize_cluster_kernel(const float* __restrict__ data, const float* __restrict_
     uint32_t word[3][kSlices] = {};
     if (j0 < n_loc) {
       float v[12];
-      load_quad<true>(s_row, lmean, nullptr, j0, n_loc, v);
+      load_quad<true>(s_row, lmean, lweight, nullptr, j0, n_loc, v);
       quad_words(v, scale, word);
     }
+    for (int d = 0; d < dst.n; ++d) {
+      int8_t* dig = dst.dig[d];
 #pragma unroll
-    for (int p = 0; p < 3; ++p)
+      for (int p = 0; p < 3; ++p)
 #pragma unroll
-      for (int sl = 0; sl < kSlices; ++sl)
-        *reinterpret_cast<uint32_t*>(dig + (int64_t)(p * kSlices + sl) * plane + t * pitch + a0 + j0) = word[p][sl];
+        for (int sl = 0; sl < kSlices; ++sl)
+          *reinterpret_cast<uint32_t*>(dig + (int64_t)(p * kSlices + sl) * plane + t * pitch + a0 + j0) = word[p][sl];
+    }
   }
   // nobody leaves while a peer may still read its maxima
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-int launch_digitize(const float* data, const float* mean, const int32_t* idx, int64_t n_t, int64_t n_a,
-                    int64_t n_sel, int64_t pitch, int8_t* dig, int32_t* expo, cudaStream_t s) {
-  return launch_digitize_rows(data, mean, idx, n_t, n_a, n_sel, pitch, dig, expo, n_t, 0, s);
+int launch_digitize(const float* data, const float* mean, const float* weight, const int32_t* idx, int64_t n_t,
+                    int64_t n_a, int64_t n_sel, int64_t pitch, int8_t* dig, int32_t* expo, cudaStream_t s) {
+  DigDests dst{};
+  dst.n = 1;
+  dst.dig[0] = dig;
+  dst.expo[0] = expo;
+  return launch_digitize_rows(data, mean, weight, idx, n_t, n_a, n_sel, pitch, dst, n_t, 0, s);
 }
 
-int launch_digitize_rows(const float* data, const float* mean, const int32_t* idx, int64_t n_rows, int64_t n_a,
-                         int64_t n_sel, int64_t pitch, int8_t* dig, int32_t* expo, int64_t n_t_total, int64_t t0,
+int launch_digitize_rows(const float* data, const float* mean, const float* weight, const int32_t* idx, int64_t n_rows,
+                         int64_t n_a, int64_t n_sel, int64_t pitch, const DigDests& dst, int64_t n_t_total, int64_t t0,
                          cudaStream_t s) {
   if (n_rows == 0) return PSA_OK;
+  DeviceGuard guard(data);
   const size_t row_bytes = (size_t)n_a * 3 * sizeof(float);
   static const bool no_stage = getenv("PSA_DIGITIZE_NO_STAGE") != nullptr;
   if (idx != nullptr && !no_stage && row_bytes <= 100 * 1024 && row_bytes % 16 == 0 &&
       (reinterpret_cast<uintptr_t>(data) & 15) == 0) {            // gathered selection, row fits: stage it
     PSA_CUDA(cudaFuncSetAttribute(digitize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_bytes));
-    digitize_kernel<true><<<(unsigned)n_rows, 256, row_bytes, s>>>(data, mean, idx, n_t_total, n_a, n_sel, pitch, dig,
-                                                                     expo, t0);
+    digitize_kernel<true><<<(unsigned)n_rows, 256, row_bytes, s>>>(data, mean, weight, idx, n_t_total, n_a, n_sel, pitch,
+                                                                     dst, t0);
     return launch_status("digitize_kernel<staged>");
   }
   if (idx == nullptr && !no_stage && row_bytes > 200 * 1024 && n_a % 4 == 0 && (reinterpret_cast<uintptr_t>(data) & 15) == 0) {
@@ -523,13 +563,14 @@ int launch_digitize_rows(const float* data, const float* mean, const int32_t* id
       attr.val.clusterDim.z = 1;
       cfg.attrs = &attr;
       cfg.numAttrs = 1;
-      PSA_CUDA(cudaLaunchKernelEx(&cfg, digitize_cluster_kernel, data, mean, n_t_total, n_a, pitch, slice_atoms, dig, expo, t0));
+      PSA_CUDA(cudaLaunchKernelEx(&cfg, digitize_cluster_kernel, data, mean, weight, n_t_total, n_a, pitch, slice_atoms, dst,
+                                  t0));
       return launch_status("digitize_cluster_kernel");
     }
   }
   // 512 threads for contiguous rows, 256 for gathered ones (bench.py on C1 / C2: 0.131 vs 0.142 ms, 0.242 vs 0.252 ms)
-  digitize_kernel<false><<<(unsigned)n_rows, idx == nullptr ? 512 : 256, 0, s>>>(data, mean, idx, n_t_total, n_a, n_sel,
-                                                                                   pitch, dig, expo, t0);
+  digitize_kernel<false><<<(unsigned)n_rows, idx == nullptr ? 512 : 256, 0, s>>>(data, mean, weight, idx, n_t_total, n_a,
+                                                                                   n_sel, pitch, dst, t0);
   return launch_status("digitize_kernel");
 }
 

@@ -74,43 +74,146 @@ int launch_intensity(const float2* sed, int64_t n_rows, int n_pol, float* out, c
 }
 
 // ---------------------------------------------------------------------------------------------
-// Inverse projection (reference: sed_calculator.py:440-441, 494-499, 533).  The spatial phase
-// k_act * (mean . khat) is formed in float32 like the reference's float32 products, the rotating
-// exponential in float64 (the reference promotes to complex128), the sum with the mean in float32.
+// Inverse projection, batched over (k, omega) points (reference: sed_calculator.py:440-441, 494-533).
+//
+// For point p and group g the reference adds   Re( A[p][g][pol] * exp(i tau_f - i k_p (mean_a . khat)) )
+// into wiggles[f][a][pol] for the atoms a of g, group after group (float64 term, float32 running sum), then
+// rescales and adds the mean.  With c_a, s_a = cos, sin of the float32 spatial phase k_p * (mean_a . khat) and
+// C_f, S_f = cos, sin of tau_f = 2 pi f / n_frames,
+//     Re(A e^{i(tau_f - x_a)}) = C_f (Ar c_a + Ai s_a) + S_f (Ar s_a - Ai c_a) = C_f U + S_f V,
+// so one float64 sincos per (atom, point) and two float64 FMAs per output value: the kernel is bound by the
+// 12 bytes it writes per (point, frame, atom).  A thread owns one atom of one point and walks the frames;
+// the groups an atom belongs to come as a CSR list in processing order (atoms in no group keep the mean).
 // ---------------------------------------------------------------------------------------------
-__global__ void ised_kernel(const float* __restrict__ mean, const double* __restrict__ amp,
-                            const float* __restrict__ khat, float k_act, double scale, int add_mean,
-                            int64_t n_a, int64_t n_frames, float* __restrict__ out) {
-  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n_a) return;
-  const float h0 = __ldg(khat), h1 = __ldg(khat + 1), h2 = __ldg(khat + 2);
-  const float m0 = mean[a * 3], m1 = mean[a * 3 + 1], m2 = mean[a * 3 + 2];
-  const float xproj = __fmaf_rn(m2, h2, __fmaf_rn(m1, h1, __fmul_rn(m0, h0)));
-  const double spatial = (double)__fmul_rn(k_act, xproj);
-  const double ar[3] = {amp[a * 6 + 0], amp[a * 6 + 2], amp[a * 6 + 4]};
-  const double ai[3] = {amp[a * 6 + 1], amp[a * 6 + 3], amp[a * 6 + 5]};
-  const float mm[3] = {m0, m1, m2};
-  const bool active = ar[0] != 0. || ai[0] != 0. || ar[1] != 0. || ai[1] != 0. || ar[2] != 0. || ai[2] != 0.;
-  for (int64_t f = blockIdx.y; f < n_frames; f += gridDim.y) {
-    double s = 0., c = 1.;
-    if (active) {
-      double tau = 6.283185307179586 * (double)f / (double)n_frames;
-      sincos(tau - spatial, &s, &c);
-    }
-#pragma unroll
-    for (int p = 0; p < 3; ++p) {
-      float w = active ? (float)(scale * (ar[p] * c - ai[p] * s)) : 0.f;
-      out[(f * n_a + a) * 3 + p] = add_mean ? __fadd_rn(mm[p], w) : w;
-    }
+constexpr int kIsedMaxFrames = 1024;            // phasor table C_f, S_f in shared memory
+
+__device__ __forceinline__ void ised_fill_phasors(double2* tab, int n_frames) {
+  for (int f = threadIdx.x; f < n_frames; f += blockDim.x) {
+    double s, c;
+    sincos(6.283185307179586 * (double)f / (double)n_frames, &s, &c);   // np.linspace(0, 2 pi, n, endpoint=False)
+    tab[f] = make_double2(c, s);
   }
 }
 
-int launch_ised(const float* mean, const double* amp, const float* khat, float k_act, double scale, int add_mean,
-                int64_t n_a, int64_t n_frames, float* out, cudaStream_t s) {
-  if (n_a == 0 || n_frames == 0) return PSA_OK;
-  dim3 grid((unsigned)((n_a + 127) / 128), (unsigned)(n_frames < 64 ? n_frames : 64));
-  ised_kernel<<<grid, 128, 0, s>>>(mean, amp, khat, k_act, scale, add_mean, n_a, n_frames, out);
-  return launch_status("ised_kernel");
+// U, V of one atom for one of its groups (float64)
+__device__ __forceinline__ void ised_uv(const IsedBatch& b, int p, int g, double ca, double sa, double (&U)[3], double (&V)[3]) {
+#pragma unroll
+  for (int pol = 0; pol < 3; ++pol) {
+    const float2 A = __ldg(b.amp + ((int64_t)p * b.n_groups + g) * 3 + pol);
+    const double ar = (double)A.x, ai = (double)A.y;
+    U[pol] = ar * ca + ai * sa;
+    V[pol] = ar * sa - ai * ca;
+  }
+}
+
+// kWrite = false: max over (frame, atom of a group, pol) of |running sum after that group| per point -> wmax[p]
+//                 (the 'auto' rescale's max_wiggle_amp_all, sed_calculator.py:502-504), nothing is stored;
+// kWrite = true : out[p][f][a][pol] = mean + ((sum / div[p]) * mul[p]) in float32, the reference's order of operations
+//                 (sed_calculator.py:517-533); div = mul = 1 leaves the sum untouched bit for bit.
+template <bool kWrite>
+__global__ void __launch_bounds__(128) ised_batch_kernel(IsedBatch b, const float* __restrict__ div,
+                                                         const float* __restrict__ mul, float* __restrict__ out,
+                                                         float* __restrict__ wmax) {
+  __shared__ double2 phasor[kIsedMaxFrames];
+  ised_fill_phasors(phasor, b.n_frames);
+  __syncthreads();
+  const int p = blockIdx.y;
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float local_max = 0.f;
+  if (a < b.n_a) {
+    const float m0 = __ldg(b.mean + a * 3), m1 = __ldg(b.mean + a * 3 + 1), m2 = __ldg(b.mean + a * 3 + 2);
+    const float xproj = __fmaf_rn(m2, __ldg(b.khat + 2), __fmaf_rn(m1, __ldg(b.khat + 1), __fmul_rn(m0, __ldg(b.khat))));
+    double sa, ca;
+    sincos((double)__fmul_rn(__ldg(b.k_act + p), xproj), &sa, &ca);
+    const int m_begin = __ldg(b.member_off + a), m_end = __ldg(b.member_off + a + 1);
+    const float mm[3] = {m0, m1, m2};
+    const float dv = kWrite ? __ldg(div + p) : 1.f, ml = kWrite ? __ldg(mul + p) : 1.f;
+    float* o = kWrite ? out + ((int64_t)p * b.n_frames * b.n_a + a) * 3 : nullptr;
+    if (m_end - m_begin == 1) {                              // the usual case: disjoint groups
+      double U[3], V[3];
+      ised_uv(b, p, __ldg(b.member_grp + m_begin), ca, sa, U, V);
+      for (int f = 0; f < b.n_frames; ++f) {
+        const double2 cs = phasor[f];
+#pragma unroll
+        for (int pol = 0; pol < 3; ++pol) {
+          const float w = (float)(cs.x * U[pol] + cs.y * V[pol]);
+          if (kWrite) o[(int64_t)f * b.n_a * 3 + pol] = __fadd_rn(mm[pol], __fmul_rn(__fdiv_rn(w, dv), ml));
+          else local_max = fmaxf(local_max, fabsf(w));
+        }
+      }
+    } else if (m_end == m_begin) {                           // not reconstructed: the mean position
+      if (kWrite)
+        for (int f = 0; f < b.n_frames; ++f)
+#pragma unroll
+          for (int pol = 0; pol < 3; ++pol)
+            o[(int64_t)f * b.n_a * 3 + pol] = __fadd_rn(mm[pol], __fmul_rn(__fdiv_rn(0.f, dv), ml));
+    } else {                                                 // overlapping groups: float32 running sum, group by group
+      for (int f = 0; f < b.n_frames; ++f) {
+        const double2 cs = phasor[f];
+        float w[3] = {0.f, 0.f, 0.f};
+        for (int m = m_begin; m < m_end; ++m) {
+          double U[3], V[3];
+          ised_uv(b, p, __ldg(b.member_grp + m), ca, sa, U, V);
+#pragma unroll
+          for (int pol = 0; pol < 3; ++pol) {
+            w[pol] = (float)((double)w[pol] + (cs.x * U[pol] + cs.y * V[pol]));
+            if (!kWrite) local_max = fmaxf(local_max, fabsf(w[pol]));   // the reference's running maximum
+          }
+        }
+        if (kWrite)
+#pragma unroll
+          for (int pol = 0; pol < 3; ++pol)
+            o[(int64_t)f * b.n_a * 3 + pol] = __fadd_rn(mm[pol], __fmul_rn(__fdiv_rn(w[pol], dv), ml));
+      }
+    }
+  }
+  if (!kWrite) {
+    for (int o2 = 16; o2 > 0; o2 >>= 1) local_max = fmaxf(local_max, __shfl_xor_sync(0xffffffffu, local_max, o2));
+    if ((threadIdx.x & 31) == 0 && local_max > 0.f) atomicMax(reinterpret_cast<int*>(wmax + p), __float_as_int(local_max));
+  }
+}
+
+static int ised_check(const IsedBatch& b) {
+  PSA_REQUIRE(b.n_frames <= kIsedMaxFrames, "psa_ised: at most %d reconstruction frames per call (got %d)", kIsedMaxFrames,
+              b.n_frames);
+  PSA_REQUIRE(b.n_points <= 65535, "psa_ised: at most 65535 points per call");
+  return PSA_OK;
+}
+
+int launch_ised_absmax(const IsedBatch& b, float* wmax, cudaStream_t s) {
+  int st = ised_check(b);
+  if (st != PSA_OK) return st;
+  PSA_CUDA(cudaMemsetAsync(wmax, 0, sizeof(float) * (size_t)(b.n_points > 0 ? b.n_points : 0), s));
+  if (b.n_a == 0 || b.n_frames == 0 || b.n_points == 0) return PSA_OK;
+  dim3 grid((unsigned)((b.n_a + 127) / 128), (unsigned)b.n_points);
+  ised_batch_kernel<false><<<grid, 128, 0, s>>>(b, nullptr, nullptr, nullptr, wmax);
+  return launch_status("ised_batch_kernel<max>");
+}
+
+int launch_ised_frames(const IsedBatch& b, const float* div, const float* mul, float* out, cudaStream_t s) {
+  int st = ised_check(b);
+  if (st != PSA_OK) return st;
+  if (b.n_a == 0 || b.n_frames == 0 || b.n_points == 0) return PSA_OK;
+  dim3 grid((unsigned)((b.n_a + 127) / 128), (unsigned)b.n_points);
+  ised_batch_kernel<true><<<grid, 128, 0, s>>>(b, div, mul, out, nullptr);
+  return launch_status("ised_batch_kernel<write>");
+}
+
+// amplitudes of the matched bins: out[p][pol] = sed[w_idx[p]][k_idx[p]][pol]  (sed_calculator.py:494-496)
+__global__ void gather_bins_kernel(const float2* __restrict__ sed, int64_t n_k, const int32_t* __restrict__ w_idx,
+                                   const int32_t* __restrict__ k_idx, int n_points, int64_t out_stride,
+                                   float2* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_points * 3) return;
+  const int p = i / 3, pol = i % 3;
+  out[(int64_t)p * out_stride + pol] = sed[((int64_t)__ldg(w_idx + p) * n_k + __ldg(k_idx + p)) * 3 + pol];
+}
+
+int launch_gather_bins(const float2* sed, int64_t n_k, const int32_t* w_idx, const int32_t* k_idx, int n_points,
+                       int64_t out_stride, float2* out, cudaStream_t s) {
+  if (n_points == 0) return PSA_OK;
+  gather_bins_kernel<<<(unsigned)((n_points * 3 + 127) / 128), 128, 0, s>>>(sed, n_k, w_idx, k_idx, n_points, out_stride, out);
+  return launch_status("gather_bins_kernel");
 }
 
 // ---------------------------------------------------------------------------------------------

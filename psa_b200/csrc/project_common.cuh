@@ -12,9 +12,12 @@ constexpr int64_t kMaxAtomsPerPass = 32768;
 // Sum over kept digit-pair classes: phase * value = T * 2^(e-36) with
 // T = c0 + 256 c1 + 256^2 c2 + 256^3 c3 (c_n = int32 accumulator of class i+j = 3+n), exact in
 // int64, rounded once to float32.
+// A row whose exponent is kExpPoison held a NaN or an infinity (or overflowed the fixed-point range): its
+// projections come out as NaN, like the reference's float arithmetic would propagate them.
 __device__ __forceinline__ float combine_classes(int32_t c0, int32_t c1, int32_t c2, int32_t c3, int e) {
   long long t = (long long)c0 + ((long long)c1 << 8) + ((long long)c2 << 16) + ((long long)c3 << 24);
-  return __ll2float_rn(t) * __int_as_float((e - 36 + 127) << 23);
+  const float scale = e == kExpPoison ? __int_as_float(0x7fc00000) : __int_as_float((e - 36 + 127) << 23);
+  return __ll2float_rn(t) * scale;
 }
 
 }  // namespace psa

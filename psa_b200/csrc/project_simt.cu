@@ -1,5 +1,5 @@
 // CUDA-core (dp4a) projection kernel.  Same contract and bit-identical output as the tcgen05 kernel
-// in project_tc.cu: it is the on-device cross-check used by the parity tests and by bring-up of the
+// in project_tc2.cu: it is the on-device cross-check used by the parity tests and by bring-up of the
 // tensor-core path (selected with PSA_PROJECT_SIMT); it is not a fallback - the Python layer always
 // asks for PSA_PROJECT_TENSOR.
 #include "project_common.cuh"

@@ -1,12 +1,13 @@
-// Projection on the tensor cores, CTA-pair version (tcgen05 cta_group::2, sm_100a).
+// Projection on the tensor cores (tcgen05 cta_group::2, sm_100a):
+//   P[row][pol][t] = sum_atoms phase[row][atom] * series[pol][t][atom]     (reference: sed_calculator.py:80-81)
+// as an exact integer contraction of int8 digit planes (common.cuh), rounded once to float32.
 //
-// Same contract, digit arithmetic and bit-exact result as project_tc.cu; the difference is the tile:
-// two CTAs of a cluster (one TPC) compute M = 256 frames x N <= 128 phase rows together.  Each CTA
+// Two CTAs of a cluster (one TPC) compute M = 256 frames x N <= 128 phase rows together.  Each CTA
 // stages its own 128 frames of trajectory digits but only HALF of the phase-digit tile (64 rows); the
-// pair's MMA reads both halves.  Shared-memory traffic per MMA drops from (128 + 128) to (128 + 64)
-// operand rows per CTA, and the stage shrinks from 64 to 48 KiB (4 stages instead of 3).  The
-// single-CTA kernel is bound by tensor-core shared-memory reads (ncu: l1tex tc wavefronts at 100 % in
-// the MMA phase with the tensor pipe at ~70 %), which is what this removes.
+// pair's MMA reads both halves.  Shared-memory traffic per MMA is (128 + 64) operand rows per CTA, the
+// stage is 48 KiB (4 stages).  A single-CTA cta_group::1 kernel (round 1, removed) was bound by
+// tensor-core shared-memory reads (ncu: l1tex tc wavefronts at 100 % in the MMA phase with the tensor
+// pipe at ~70 %) and 5-8 % slower.
 //
 // Protocol (rank 0 = leader of the pair):
 //   producers (warp 0 lane 0 of BOTH CTAs)   TMA into their own smem with .cta_group::2, completing
@@ -101,7 +102,7 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
       ::"r"(smem_u32(bar)), "h"((uint16_t)3)
       : "memory");
 }
-// see project_tc.cu: elect.sync keeps the issue code straight-line
+// elect.sync (instead of lane == 0) keeps the issue code straight-line
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -358,6 +359,7 @@ int launch_project_tc2(const int8_t* adig, int64_t rows, int64_t rows_alloc, con
                        cudaStream_t s) {
   using namespace tc2;
   if (rows == 0 || n_t == 0) return PSA_OK;
+  DeviceGuard guard(P);
   PSA_REQUIRE(n_sel > 0, "psa_project: empty atom selection");
   PSA_REQUIRE(rows < (1 << 30) && n_t < (1 << 30) && n_sel < (1 << 30), "psa_project: extent too large");
   CUtensorMap map_phase, map_traj;
@@ -366,11 +368,8 @@ int launch_project_tc2(const int8_t* adig, int64_t rows, int64_t rows_alloc, con
   st = make_map(&map_traj, bdig, n_sel, pitch, n_t, n_t, 3 * kSlices, BM);
   if (st != PSA_OK) return st;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    PSA_CUDA(cudaFuncSetAttribute(project_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  // per device and per context: set on every launch (a process may drive several GPUs from several threads)
+  PSA_CUDA(cudaFuncSetAttribute(project_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   int dev = 0, sms = 0;
   PSA_CUDA(cudaGetDevice(&dev));
   PSA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -3,18 +3,29 @@
 The SED path shards naturally by k-point - every output column depends on the whole trajectory
 but on no other k (reference: src/psa/core/sed_calculator.py:287-327 already loops over independent
 k-chunks).  So there is exactly one exchange step: the k-independent device state (float32 mean
-positions and the int8 digit planes of the projected series) is produced once on the source rank
-and broadcast with NCCL over NVLink; every rank then projects + transforms its own contiguous
-k-slice with no further communication, and the slices are gathered on the destination rank.
+positions and the int8 digit planes of the projected series) has to reach every rank.  Two ways:
 
-``torch.distributed`` is plumbing here (process group, broadcast, gather); the arithmetic is the
-same C-ABI path as on one GPU.  The host-side pieces (slice arithmetic, gather re-assembly) work
-on any backend and are covered by world_size-2 ``gloo`` tests on CPU.
+* ``ingest="broadcast"``: the source rank uploads and ingests everything, one NCCL broadcast.
+* ``ingest="sliced"``: every rank uploads 1/N of the frames over its own PCIe link.  The float32 mean is an
+  ordered running sum handed from rank to rank; the digit planes are produced by ONE kernel per rank that stores
+  every digitised row into all ranks' planes through NVLink (CUDA-IPC mapped peer memory,
+  ``psa_digitize_rows_peers``) - the all-gather is fused into the producing kernel.  When peer mapping is not
+  available the rows are exchanged with NCCL all-gathers instead (same bits).
+
+Every rank then projects + transforms its own contiguous k-slice with no further communication and copies its
+spectra straight into its column slice of ONE result array in shared, page-locked host memory
+(:class:`SharedHostArray`) - every PCIe link carries 1/N of the result, nothing funnels through the source rank.
+
+``torch.distributed`` is plumbing here (process group, small collectives); the arithmetic is the same C-ABI
+path as on one GPU.  The host-side pieces (slice arithmetic, the ordered chain, shared result array) work on
+any backend and are covered by world_size-2 ``gloo`` tests on CPU.
 """
 from __future__ import annotations
 
+import ctypes
 import os
-from typing import List, Optional, Sequence, Tuple
+from multiprocessing import resource_tracker, shared_memory
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -50,6 +61,69 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, world, local
 
 
+# ---------------------------------------------------------------------------------------------- shared host result
+class SharedHostArray:
+    """One host array mapped by every rank of the box (POSIX shared memory), page-locked for CUDA in each process.
+
+    Collective: every rank of ``group`` constructs it with the same shape/dtype.  ``array`` is the NumPy view,
+    ``ptr`` its address.  The segment is unlinked as soon as every rank has mapped it, so nothing is left behind
+    in /dev/shm if a process dies; the memory lives until the last mapping closes."""
+
+    def __init__(self, shape: Sequence[int], dtype, src: int = 0, group=None, register: Optional[bool] = None):
+        self.shape, self.dtype = tuple(int(s) for s in shape), np.dtype(dtype)
+        nbytes = max(1, int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize)
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        rank = dist.get_rank(group) if distributed else src
+        if rank == src:
+            self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+        if distributed:
+            box = [self._shm.name if rank == src else None]
+            dist.broadcast_object_list(box, src=src, group=group)
+            if rank != src:
+                self._shm = shared_memory.SharedMemory(name=box[0])
+                try:        # the creator owns the name; keep Python's tracker from unlinking it a second time at exit
+                    resource_tracker.unregister(self._shm._name, "shared_memory")
+                except Exception:
+                    pass
+            dist.barrier(group=group)                    # everybody has mapped the segment
+        if rank == src:
+            self._shm.unlink()
+        self.array = np.ndarray(self.shape, self.dtype, buffer=self._shm.buf)
+        self.ptr = ctypes.addressof(ctypes.c_char.from_buffer(self._shm.buf))
+        self.nbytes = nbytes
+        self._registered = False
+        if register is None:
+            register = torch.cuda.is_available()
+        if register:
+            from . import _lib
+            _lib.call("psa_host_register", self.ptr, nbytes)
+            self._registered = True
+
+    def close(self) -> None:
+        if getattr(self, "_shm", None) is None:
+            return
+        if self._registered:
+            from . import _lib
+            try:
+                _lib.call("psa_host_unregister", self.ptr)
+            except Exception:
+                pass
+            self._registered = False
+        self.array = None
+        try:
+            self._shm.close()
+        except BufferError:       # a NumPy view handed to the caller is still alive: the mapping stays until it goes
+            pass
+        self._shm = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------- small collectives
 def broadcast_tensors(tensors: Sequence[Optional[torch.Tensor]], metas: Optional[List[Tuple]], src: int,
                       device: torch.device, group=None) -> List[torch.Tensor]:
     """Broadcast a list of tensors whose shapes/dtypes only ``src`` knows.  Returns the tensors on every rank."""
@@ -66,7 +140,8 @@ def broadcast_tensors(tensors: Sequence[Optional[torch.Tensor]], metas: Optional
 
 def gather_k_slices(local: torch.Tensor, n_k_total: int, dst: int = 0, group=None) -> Optional[torch.Tensor]:
     """Assemble per-rank results ``(n_f, n_k_local, ...)`` (contiguous k-slices in rank order, as produced
-    with :func:`shard_range`) into ``(n_f, n_k_total, ...)`` on ``dst``; other ranks get ``None``."""
+    with :func:`shard_range`) into ``(n_f, n_k_total, ...)`` on ``dst``; other ranks get ``None``.  (Device-resident
+    gather for callers that want the whole result on one GPU; ``calculate_sharded`` does not funnel through it.)"""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     widths = [b - a for a, b in (shard_range(n_k_total, r, world) for r in range(world))]
     w_max = max(widths)
@@ -93,51 +168,6 @@ def gather_k_slices(local: torch.Tensor, n_k_total: int, dst: int = 0, group=Non
     return full
 
 
-def sliced_ingest(calc, proj_groups, local_rows=None, group=None) -> None:
-    """k-independent state from a trajectory whose FRAMES are spread over the ranks.
-
-    Rank r uploads only frames ``shard_range(n_t, r, world)`` - 1/N of the bytes over its own PCIe link -
-    and the ranks then build the shared state together:
-
-    * mean positions: the float32 sum of a column must run in frame order to stay bit-identical with
-      NumPy, so the running sums travel down the ranks (one (n_atoms, 3) message per hop); the last rank
-      divides and broadcasts the mean;
-    * digit planes: every frame row is digitised independently (its own exponent), each rank handles its
-      rows and the row blocks are exchanged with one all-gather (or broadcast) per plane.
-
-    ``local_rows = (positions[t0:t1], velocities[t0:t1])`` when this process holds nothing but its range;
-    otherwise the range is sliced out of ``calc.traj``.  On return every rank's device trajectory has the
-    mean and the digit planes of ``proj_groups`` installed, exactly as after the broadcast ingest.
-    """
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    eng, dtraj = calc.engine, calc.device_trajectory
-    # skip only if EVERY rank already holds the state (a rank that computed something on its own must not
-    # leave the others waiting in the chain)
-    ready = torch.tensor([1 if dtraj.has_state(proj_groups, calc.use_displacements) else 0], device=eng.device)
-    dist.all_reduce(ready, op=dist.ReduceOp.MIN, group=group)
-    if int(ready.item()) == 1:
-        return
-    n_t, n_a = dtraj.n_t, dtraj.n_a
-    bounds = [shard_range(n_t, r, world) for r in range(world)]
-    t0, t1 = bounds[rank]
-    disp = calc.use_displacements
-    pos_rows = dtraj.upload_rows("pos", t0, t1, None if local_rows is None else local_rows[0])
-    data_rows = pos_rows if disp else dtraj.upload_rows("vel", t0, t1, None if local_rows is None else local_rows[1])
-
-    acc = chain_running_sum(torch.zeros((n_a, 3), dtype=torch.float32, device=eng.device),
-                            lambda a, last: eng.mean_accumulate(pos_rows, a, n_t if last else 0), group)
-    dtraj.install_mean(acc)
-
-    for g in proj_groups:
-        idx, idx_dev, n_sel = dtraj.selection(g, disp)
-        pitch = int(eng_pitch(n_sel))
-        dig = eng.empty((3, 4, n_t, pitch), torch.int8)
-        expo = eng.empty((3, n_t), torch.int32)
-        eng.digitize_rows(data_rows, acc if disp else None, idx_dev, n_sel, pitch, dig, expo, n_t, t0)
-        exchange_row_blocks(list(dig.view(12, n_t, pitch).unbind(0)) + list(expo.unbind(0)), bounds, group)
-        dtraj.install_group(idx, disp, dig, expo)
-
-
 def chain_running_sum(acc: torch.Tensor, accumulate, group=None) -> torch.Tensor:
     """Ordered reduction over the ranks: rank 0 starts from ``acc``, every rank continues the running value
     with ``accumulate(acc, is_last_rank)`` (in place) and hands it to the next one; the last rank's result
@@ -156,7 +186,8 @@ def chain_running_sum(acc: torch.Tensor, accumulate, group=None) -> torch.Tensor
 def exchange_row_blocks(planes, bounds, group=None) -> None:
     """Every tensor in ``planes`` has its leading axis split over the ranks as ``bounds[r] = (a, b)``; each
     rank has filled its own block.  Afterwards every rank holds every block (in place): one all-gather
-    per plane when the blocks have equal length, one broadcast per (plane, rank) otherwise."""
+    per plane when the blocks have equal length, one broadcast per (plane, rank) otherwise.  (The NCCL fallback
+    of the fused peer-store exchange.)"""
     rank = dist.get_rank(group)
     t0, t1 = bounds[rank]
     equal = all(b - a == t1 - t0 for a, b in bounds)
@@ -174,66 +205,248 @@ def eng_pitch(n_sel: int) -> int:
     return int(_lib.load().psa_pitch(n_sel))
 
 
+# ---------------------------------------------------------------------------------------------- peer-mapped planes
+class PeerPlanes:
+    """Digit planes + exponents of one atom selection on this rank, plus the same buffers of every peer rank mapped
+    into this process through CUDA IPC.  Built once per (calculator, selection) and reused by every ingest: the
+    buffers must outlive the peers' mappings, so they are owned here and never returned to the allocator."""
+
+    def __init__(self, eng, n_t: int, pitch: int, group=None):
+        from . import _lib
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.dig = eng.empty((3, 4, n_t, pitch), torch.int8)
+        self.expo = eng.empty((3, n_t), torch.int32)
+        mine, failed = [], None
+        try:
+            for t in (self.dig, self.expo):
+                handle = (ctypes.c_char * 64)()
+                off = ctypes.c_int64(0)
+                _lib.call("psa_ipc_export", t.data_ptr(), ctypes.addressof(handle), ctypes.addressof(off))
+                mine.append((bytes(handle), int(off.value)))
+        except (RuntimeError, ValueError, NotImplementedError) as exc:
+            mine, failed = None, exc
+        everyone: List = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)           # every rank reaches this, failed or not
+        self._opened: Dict[bytes, int] = {}
+        if any(e is None for e in everyone):
+            raise RuntimeError(f"CUDA IPC export failed on a rank ({failed})")
+        ptrs = [[0] * self.world, [0] * self.world]
+        for r, pair in enumerate(everyone):
+            for which, (handle, off) in enumerate(pair):
+                if r == self.rank:
+                    ptrs[which][r] = (self.dig, self.expo)[which].data_ptr()
+                    continue
+                base = self._opened.get(handle)
+                if base is None:
+                    out = ctypes.c_void_p(0)
+                    buf = ctypes.create_string_buffer(handle, 64)
+                    _lib.call("psa_ipc_open", ctypes.addressof(buf), ctypes.addressof(out))
+                    base = self._opened[handle] = int(out.value)
+                ptrs[which][r] = base + off
+        self.dig_ptrs = (ctypes.c_void_p * self.world)(*ptrs[0])
+        self.expo_ptrs = (ctypes.c_void_p * self.world)(*ptrs[1])
+
+    def close(self) -> None:
+        from . import _lib
+        for base in self._opened.values():
+            try:
+                _lib.call("psa_ipc_close", base)
+            except Exception:
+                pass
+        self._opened = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _peer_planes(calc, key, n_t: int, pitch: int, group=None) -> Optional[PeerPlanes]:
+    """The cached :class:`PeerPlanes` of a selection, or ``None`` when peer mapping is not possible on every rank
+    (not NCCL/CUDA, more than 8 ranks, IPC refused - e.g. an allocator using virtual-memory segments)."""
+    cache = calc.__dict__.setdefault("_peer_planes", {})
+    if key in cache:
+        return cache[key]
+    world = dist.get_world_size(group)
+    planes, ok = None, 1
+    if os.environ.get("PSA_B200_PEER_STORES", "1") == "0" or world > 8 or dist.get_backend(group) != "nccl":
+        ok = 0
+    flag = torch.tensor([ok], device=calc.engine.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 1:
+        try:
+            planes = PeerPlanes(calc.engine, n_t, pitch, group)
+        except (RuntimeError, ValueError, NotImplementedError):
+            planes = None
+        flag = torch.tensor([1 if planes is not None else 0], device=calc.engine.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            planes = None
+    cache[key] = planes
+    return planes
+
+
+def _stream_fence(device, group=None) -> None:
+    """Order the ranks' streams: nothing queued after this call on any rank starts before everything queued before
+    it on every rank has finished (a one-element all-reduce; stream-ordered, the host does not wait)."""
+    dist.all_reduce(torch.zeros(1, device=device), group=group)
+
+
+def sliced_ingest(calc, proj_groups, local_rows=None, group=None, marks=None) -> None:
+    """k-independent state from a trajectory whose FRAMES are spread over the ranks.
+
+    Rank r uploads only frames ``shard_range(n_t, r, world)`` - 1/N of the bytes over its own PCIe link -
+    and the ranks then build the shared state together:
+
+    * mean positions: the float32 sum of a column must run in frame order to stay bit-identical with
+      NumPy, so the running sums travel down the ranks (one (n_atoms, 3) message per hop); the last rank
+      divides and broadcasts the mean;
+    * digit planes: every frame row is digitised independently (its own exponent); each rank's kernel stores its
+      rows into every rank's planes through NVLink (fallback: NCCL all-gather per plane).
+
+    ``local_rows = (positions[t0:t1], velocities[t0:t1])`` (host arrays or CUDA tensors) when this process holds
+    nothing but its range; otherwise the range is sliced out of ``calc.traj``.  On return every rank's device
+    trajectory has the mean and the digit planes of ``proj_groups`` installed, exactly as after a one-GPU ingest.
+    ``marks``: optional callable ``marks(name)`` recording a stage boundary on the stream (bench breakdown).
+    """
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    eng, dtraj = calc.engine, calc.device_trajectory
+    mark = marks or (lambda name: None)
+    # skip only if EVERY rank already holds the state (a rank that computed something on its own must not
+    # leave the others waiting in the chain)
+    ready = torch.tensor([1 if dtraj.has_state(proj_groups, calc.use_displacements) else 0], device=eng.device)
+    dist.all_reduce(ready, op=dist.ReduceOp.MIN, group=group)
+    if int(ready.item()) == 1:
+        return
+    n_t, n_a = dtraj.n_t, dtraj.n_a
+    bounds = [shard_range(n_t, r, world) for r in range(world)]
+    t0, t1 = bounds[rank]
+    disp = calc.use_displacements
+    pos_rows = dtraj.upload_rows("pos", t0, t1, None if local_rows is None else local_rows[0])
+    data_rows = pos_rows if disp else dtraj.upload_rows("vel", t0, t1, None if local_rows is None else local_rows[1])
+    mark("upload")
+
+    acc = chain_running_sum(torch.zeros((n_a, 3), dtype=torch.float32, device=eng.device),
+                            lambda a, last: eng.mean_accumulate(pos_rows, a, n_t if last else 0), group)
+    dtraj.install_mean(acc)
+    mark("mean_chain")
+
+    for g in proj_groups:
+        idx, idx_dev, n_sel = dtraj.selection(g, disp)
+        pitch = int(eng_pitch(n_sel))
+        key = dtraj._group_key(g, disp)[0]
+        peers = _peer_planes(calc, (key, n_t, pitch), n_t, pitch, group)
+        if peers is not None:
+            _stream_fence(eng.device, group)            # nobody still projects from the planes of a previous ingest
+            eng._run("psa_digitize_rows_peers", 1, data_rows.data_ptr(), acc.data_ptr() if disp else None,
+                     None if dtraj.weight is None else dtraj.weight.data_ptr(),
+                     None if idx_dev is None else idx_dev.data_ptr(), t1 - t0, n_a, n_sel, pitch,
+                     ctypes.addressof(peers.dig_ptrs), ctypes.addressof(peers.expo_ptrs), world, n_t, t0, eng.stream())
+            _stream_fence(eng.device, group)            # every rank's rows have landed everywhere
+            dig, expo = peers.dig, peers.expo
+        else:
+            dig = eng.empty((3, 4, n_t, pitch), torch.int8)
+            expo = eng.empty((3, n_t), torch.int32)
+            eng.digitize_rows(data_rows, acc if disp else None, idx_dev, n_sel, pitch, dig, expo, n_t, t0, dtraj.weight)
+            exchange_row_blocks(list(dig.view(12, n_t, pitch).unbind(0)) + list(expo.unbind(0)), bounds, group)
+        dtraj.install_group(idx, disp, dig, expo)
+    mark("digitize_exchange")
+
+
+def shared_result(calc, shape, np_dtype, src: int = 0, group=None) -> SharedHostArray:
+    """The shared page-locked result array of this shape, cached on the calculator (mapping + pinning a multi-GB
+    array is setup, like allocating the pinned input buffers)."""
+    cache = calc.__dict__.setdefault("_shared_results", {})
+    key = (tuple(shape), np.dtype(np_dtype).str)
+    shared = cache.get(key)
+    if shared is None:
+        shared = cache[key] = SharedHostArray(shape, np_dtype, src=src, group=group)
+    return shared
+
+
 def calculate_sharded(calc, k_points_mags: np.ndarray, k_vectors_3d: np.ndarray, basis_atom_indices=None,
                       basis_atom_types=None, summation_mode: str = "coherent", k_grid_shape=None, src: int = 0,
-                      group=None, ingest: str = "broadcast", local_rows=None):
+                      group=None, ingest: str = "broadcast", local_rows=None, k_chunk_size: int = 500,
+                      timings: Optional[Dict[str, float]] = None):
     """``SEDCalculator.calculate`` over all ranks of the process group.
 
     Every rank calls this with a calculator built on a trajectory of the right *shape*.  With
     ``ingest="broadcast"`` only ``src`` needs real positions/velocities (the others may hold zero-stride
     placeholders): it uploads and ingests everything and broadcasts the result.  With ``ingest="sliced"``
     every rank holds (at least) its own range of frames and uploads just that, see :func:`sliced_ingest`.
-    Returns the ``SED`` on ``src`` and ``None`` elsewhere.
+    Every rank streams its k-slice of the spectra into ONE result array in shared page-locked host memory.
+    Returns the ``SED`` on ``src`` (its ``sed`` is a view of that shared array, valid until the next call with
+    the same result shape on this calculator) and ``None`` elsewhere.
+    ``timings`` (a dict) receives a per-stage breakdown in milliseconds of this rank's stream.
     """
     from . import groups as grp
-    from .engine import sed_on_device
+    from .engine import HostTarget, sed_on_device
     from .sed import SED
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return calc.calculate(k_points_mags, k_vectors_3d, basis_atom_indices, basis_atom_types,
-                              summation_mode, k_grid_shape)
+                              summation_mode, k_grid_shape, k_chunk_size)
     if summation_mode not in ("coherent", "incoherent"):
         raise ValueError(f"summation_mode must be 'coherent' or 'incoherent', got {summation_mode}")
+    if ingest not in ("broadcast", "sliced"):
+        raise ValueError(f"ingest must be 'broadcast' or 'sliced', got {ingest}")
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     traj = calc.traj
     eng, dtraj = calc.engine, calc.device_trajectory
     groups = grp.resolve_sed_groups(traj.types, traj.n_atoms, basis_atom_indices, basis_atom_types, summation_mode)
     complex_out, proj_groups = grp.plan_sed_groups(groups, summation_mode)
+    k_vecs = np.ascontiguousarray(np.asarray(k_vectors_3d, dtype=np.float32).reshape(-1, 3))
+    n_k, n_t = k_vecs.shape[0], traj.n_frames
 
-    if ingest not in ("broadcast", "sliced"):
-        raise ValueError(f"ingest must be 'broadcast' or 'sliced', got {ingest}")
+    events: List[Tuple[str, torch.cuda.Event]] = []
+
+    def mark(name: str) -> None:
+        if timings is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(eng.device))
+            events.append((name, ev))
+
     with torch.cuda.device(eng.device):
+        # the result array, shared by the ranks and page-locked (cached per shape)
+        shape = (n_t, n_k, 3) if complex_out else (n_t, n_k)
+        shared = shared_result(calc, shape, np.complex64 if complex_out else np.float32, src, group)
+        mark("start")
+        # 1. k-independent state on every rank
         if ingest == "sliced":
-            sliced_ingest(calc, proj_groups, local_rows, group)
-        # 1. k-independent state: built on src, broadcast once
-        tensors: List[Optional[torch.Tensor]] = []
-        metas: List[Tuple] = []
-        if ingest == "sliced":
-            got = []
-        elif rank == src:
-            tensors.append(dtraj.mean)
-            for g in proj_groups:
-                _, _, _, dig, expo = dtraj.group(g, calc.use_displacements)
-                tensors += [dig, expo]
-            metas = [(tuple(t.shape), t.dtype) for t in tensors]
-        if ingest == "broadcast":
+            sliced_ingest(calc, proj_groups, local_rows, group, marks=mark)
+        else:
+            tensors: List[Optional[torch.Tensor]] = []
+            metas: List[Tuple] = []
+            if rank == src:
+                tensors.append(dtraj.mean)
+                for g in proj_groups:
+                    _, _, _, dig, expo = dtraj.group(g, calc.use_displacements)
+                    tensors += [dig, expo]
+                metas = [(tuple(t.shape), t.dtype) for t in tensors]
             got = broadcast_tensors(tensors, metas, src, eng.device, group)
-        if ingest == "broadcast" and rank != src:
-            dtraj.install_mean(got[0])
-            for i, g in enumerate(proj_groups):
-                dtraj.install_group(g, calc.use_displacements, got[1 + 2 * i], got[2 + 2 * i])
+            if rank != src:
+                dtraj.install_mean(got[0])
+                for i, g in enumerate(proj_groups):
+                    dtraj.install_group(g, calc.use_displacements, got[1 + 2 * i], got[2 + 2 * i])
+            mark("ingest_broadcast")
 
-        # 2. every rank: its contiguous k-slice, no communication
-        k_vecs = np.ascontiguousarray(np.asarray(k_vectors_3d, dtype=np.float32).reshape(-1, 3))
-        n_k = k_vecs.shape[0]
+        # 2. every rank: its contiguous k-slice, no communication; spectra stream out over this rank's own PCIe link
         k0, k1 = shard_range(n_k, rank, world)
-        local = sed_on_device(dtraj, k_vecs[k0:k1], proj_groups, complex_out, calc.use_displacements)
-
-        # 3. gather on src
-        full = gather_k_slices(local, n_k, dst=src, group=group)
-        if rank != src:
-            return None
-        sed_host = calc._to_host(full)
-    freqs = np.fft.fftfreq(traj.n_frames, d=calc.dt_ps)
-    return SED(sed_host, freqs, k_points_mags, k_vectors_3d, k_grid_shape=k_grid_shape,
+        if k1 > k0 and n_t > 0:
+            sed_on_device(dtraj, k_vecs[k0:k1], proj_groups, complex_out, calc.use_displacements, k_chunk=k_chunk_size,
+                          host_out=HostTarget(shared.ptr, n_k, k0, n_t, shared))
+        mark("compute")
+        eng.copy_stream.synchronize()
+        torch.cuda.current_stream(eng.device).synchronize()
+        if timings is not None:
+            mark("result_drain")
+            torch.cuda.current_stream(eng.device).synchronize()
+            for (_, a), (name, b) in zip(events[:-1], events[1:]):
+                timings[name] = timings.get(name, 0.0) + a.elapsed_time(b)
+        dist.barrier(group=group)                          # every slice is in the shared array
+    if rank != src:
+        return None
+    freqs = np.fft.fftfreq(n_t, d=calc.dt_ps)
+    return SED(shared.array, freqs, k_points_mags, k_vectors_3d, k_grid_shape=k_grid_shape,
                is_complex=complex_out, phase=None, context=calc._context(groups))

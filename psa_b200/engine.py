@@ -20,7 +20,8 @@ from __future__ import annotations
 import hashlib
 import os
 import threading
-from typing import Dict, List, Optional, Sequence, Tuple
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -28,7 +29,30 @@ import torch
 from . import _lib
 
 K_CHUNK_CAP = 1024            # k-points per chunk (2048 projection rows = 16 row tiles)
+K_CHUNK_REFERENCE_DEFAULT = 500   # the reference's default k_chunk_size (sed_calculator.py:185)
+
+
+def effective_k_chunk(k_chunk_size: int, n_k: int) -> int:
+    """k-points per projection launch.  The reference's ``k_chunk_size`` bounds the size of its temporaries; here
+    the results do not depend on the chunking at all (the contraction is exact), so the knob is only honoured as a
+    memory limit when the caller LOWERS it below the reference's default; at the default or above, chunks are as
+    large as the projection scratch allows (fewer passes over the digit planes, fewer launch tails)."""
+    k_chunk_size = max(1, int(k_chunk_size))
+    cap = K_CHUNK_CAP if k_chunk_size >= K_CHUNK_REFERENCE_DEFAULT else k_chunk_size
+    return max(1, min(cap, n_k, K_CHUNK_CAP))
 _UPLOAD_CHUNK_BYTES = 256 << 20
+
+
+@dataclass
+class HostTarget:
+    """Where a streamed result goes: a page-locked host array of shape ``(n_rows, n_k_total[, 3])`` of which one call
+    fills the columns ``[k_offset, k_offset + n_k)`` (reference: ``full_sed_data[:, k0:k1]``, sed_calculator.py:310, 325).
+    On several GPUs every rank targets its own column slice of ONE array in shared host memory."""
+    ptr: int                 # host address of element [0][0]
+    n_k_total: int
+    k_offset: int
+    n_rows: int
+    keepalive: Any = None    # whatever owns the memory
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -46,7 +70,7 @@ class Engine:
         self.device = torch.device("cuda", device)
         _lib.check(_lib.load().psa_device_check(device))
         if project_impl is None:
-            project_impl = int(os.environ.get("PSA_B200_PROJECT_IMPL", _lib.PROJECT_TENSOR_PAIR))
+            project_impl = int(os.environ.get("PSA_B200_PROJECT_IMPL", _lib.PROJECT_TENSOR))
         self.project_impl = project_impl
         self._plans: Dict[int, torch.Tensor] = {}
         self._fft_ws: Optional[torch.Tensor] = None
@@ -105,12 +129,12 @@ class Engine:
         return mean
 
     def digitize(self, data: torch.Tensor, mean: Optional[torch.Tensor], idx: Optional[torch.Tensor],
-                 n_sel: int) -> Tuple[torch.Tensor, torch.Tensor, int]:
+                 n_sel: int, weight: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, int]:
         n_t, n_a, _ = data.shape
         pitch = int(_lib.load().psa_pitch(n_sel))
         dig = self.empty((3, 4, n_t, pitch), torch.int8)
         expo = self.empty((3, n_t), torch.int32)
-        self._run("psa_digitize", 1, data.data_ptr(), _ptr(mean), _ptr(idx), n_t, n_a, n_sel, pitch,
+        self._run("psa_digitize", 1, data.data_ptr(), _ptr(mean), _ptr(weight), _ptr(idx), n_t, n_a, n_sel, pitch,
                   dig.data_ptr(), expo.data_ptr(), self.stream())
         return dig, expo, pitch
 
@@ -123,9 +147,10 @@ class Engine:
         return out
 
     def digitize_rows(self, rows: torch.Tensor, mean: Optional[torch.Tensor], idx: Optional[torch.Tensor], n_sel: int,
-                      pitch: int, dig: torch.Tensor, expo: torch.Tensor, n_t_total: int, t0: int) -> None:
+                      pitch: int, dig: torch.Tensor, expo: torch.Tensor, n_t_total: int, t0: int,
+                      weight: Optional[torch.Tensor] = None) -> None:
         n_rows, n_a, _ = rows.shape
-        self._run("psa_digitize_rows", 1, rows.data_ptr(), _ptr(mean), _ptr(idx), n_rows, n_a, n_sel, pitch,
+        self._run("psa_digitize_rows", 1, rows.data_ptr(), _ptr(mean), _ptr(weight), _ptr(idx), n_rows, n_a, n_sel, pitch,
                   dig.data_ptr(), expo.data_ptr(), n_t_total, t0, self.stream())
 
     def phase_digits(self, kvecs: torch.Tensor, mean: torch.Tensor, idx: Optional[torch.Tensor], n_sel: int,
@@ -156,7 +181,8 @@ class Engine:
         return plan
 
     def fft_sed(self, P: torch.Tensor, n_groups: int, group_stride: int, n_k: int, n_t: int, ldp: int,
-                mode: int, out: torch.Tensor, n_k_total: int, k_offset: int) -> None:
+                mode: int, out: torch.Tensor, n_k_total: int, k_offset: int,
+                window: Optional[torch.Tensor] = None) -> None:
         plan = self.fft_plan(n_t)
         ws_bytes = int(_lib.load().psa_fft_workspace_bytes(n_t, n_k, n_groups))
         ws = None
@@ -165,7 +191,8 @@ class Engine:
                 self._fft_ws = self.empty((ws_bytes,), torch.uint8)
             ws = self._fft_ws
         self._run("psa_fft_sed", 1 if ws is None else 2, P.data_ptr(), n_groups, group_stride, n_k, n_t, ldp,
-                  plan.data_ptr(), _ptr(ws), ws_bytes, mode, out.data_ptr(), n_k_total, k_offset, self.stream())
+                  plan.data_ptr(), _ptr(ws), ws_bytes, _ptr(window), mode, out.data_ptr(), n_k_total, k_offset,
+                  self.stream())
 
     def chiral_phase(self, z1: torch.Tensor, z2: torch.Tensor, n: int, stride1: int, stride2: int, opt: str,
                      out: torch.Tensor) -> None:
@@ -183,10 +210,17 @@ class Engine:
 class DeviceTrajectory:
     """A trajectory resident in HBM plus everything derived from it that is k-independent."""
 
-    def __init__(self, engine: Engine, positions: np.ndarray, velocities: np.ndarray):
+    def __init__(self, engine: Engine, positions: np.ndarray, velocities: np.ndarray,
+                 weight: Optional[np.ndarray] = None, window: Optional[np.ndarray] = None):
+        """``weight``: per-atom float32 factor multiplied into the projected series (sqrt(mass) for the README's mass
+        weighting; ``None`` = the reference's unweighted SED).  ``window``: float32 taper over the frames applied
+        before the time FFT (``None`` = rectangular, the reference)."""
         self.engine = engine
         self.n_t, self.n_a = positions.shape[0], positions.shape[1]
         self._host = {"pos": positions, "vel": velocities}
+        self._weight_host, self._window_host = weight, window
+        self._weight_dev: Optional[torch.Tensor] = None
+        self._window_dev: Optional[torch.Tensor] = None
         self._dev: Dict[str, torch.Tensor] = {}
         self._mean: Optional[torch.Tensor] = None
         self._groups: Dict[Tuple, Tuple] = {}
@@ -255,6 +289,18 @@ class DeviceTrajectory:
         if idx is None:
             return idx, None, self.n_a
         return idx, self._index_tensor(key, idx), int(idx.size)
+
+    @property
+    def weight(self) -> Optional[torch.Tensor]:
+        if self._weight_host is not None and self._weight_dev is None:
+            self._weight_dev = self.engine.upload_small(np.ascontiguousarray(self._weight_host, np.float32))
+        return self._weight_dev
+
+    @property
+    def window(self) -> Optional[torch.Tensor]:
+        if self._window_host is not None and self._window_dev is None:
+            self._window_dev = self.engine.upload_small(np.ascontiguousarray(self._window_host, np.float32))
+        return self._window_dev
 
     @property
     def positions(self) -> torch.Tensor:
@@ -329,9 +375,9 @@ class DeviceTrajectory:
                 idx_dev = self._index_tensor(key, idx)
                 n_sel = int(idx.size)
             if use_displacements:
-                dig, expo, pitch = eng.digitize(self.positions, self.mean, idx_dev, n_sel)
+                dig, expo, pitch = eng.digitize(self.positions, self.mean, idx_dev, n_sel, self.weight)
             else:
-                dig, expo, pitch = eng.digitize(self.velocities, None, idx_dev, n_sel)
+                dig, expo, pitch = eng.digitize(self.velocities, None, idx_dev, n_sel, self.weight)
             entry = (idx_dev, n_sel, pitch, dig, expo)
             self._groups[key] = entry
             return entry
@@ -339,19 +385,19 @@ class DeviceTrajectory:
 
 def sed_on_device(traj: DeviceTrajectory, k_vecs: np.ndarray, groups: Sequence[Optional[np.ndarray]],
                   complex_out: bool, use_displacements: bool, k_chunk: int = K_CHUNK_CAP,
-                  host_out: Optional[torch.Tensor] = None, n_rows: Optional[int] = None) -> Optional[torch.Tensor]:
+                  host_out: Optional[HostTarget] = None) -> Optional[torch.Tensor]:
     """Run the projection + FFT pipeline; returns the device-resident result.
 
     ``groups``: atom index arrays (``None`` = all atoms).  ``complex_out`` -> complex64
     ``(n_t, n_k, 3)`` from the single group; otherwise float32 ``(n_t, n_k)`` summed over groups.
 
-    With ``host_out`` (a pinned host tensor of the result's shape) nothing result-sized is kept on the
+    With ``host_out`` (a :class:`HostTarget`: page-locked host memory) nothing result-sized is kept on the
     device: every k-chunk is transformed into one of two chunk buffers and copied into its column slice
-    of ``host_out`` on a side stream while the next chunk is projected (the reference fills
+    of the host array on a side stream while the next chunk is projected (the reference fills
     ``full_sed_data[:, k0:k1]`` chunk by chunk as well, sed_calculator.py:287-327).  Returns ``None``;
-    the caller synchronises ``traj.engine.copy_stream`` before reading ``host_out``.  ``n_rows`` limits the
-    streamed copy to the first ``n_rows`` frequency rows (``host_out`` then has that many rows): fftfreq
-    order puts 0 <= f <= f_max first, so a frequency crop never leaves the device.
+    the caller synchronises ``traj.engine.copy_stream`` before reading the array.  ``host_out.n_rows`` limits the
+    streamed copy to the first rows: fftfreq order puts 0 <= f <= f_max first, so a frequency crop never
+    leaves the device.
     """
     eng = traj.engine
     n_t, n_k = traj.n_t, int(k_vecs.shape[0])
@@ -359,14 +405,13 @@ def sed_on_device(traj: DeviceTrajectory, k_vecs: np.ndarray, groups: Sequence[O
     dtype = torch.complex64 if complex_out else torch.float32
     if complex_out:
         assert len(groups) == 1
-    n_rows = n_t if n_rows is None else max(0, min(int(n_rows), n_t))
-    if host_out is not None:
-        assert tuple(host_out.shape) == (n_rows,) + shape[1:] and host_out.dtype == dtype and host_out.is_pinned()
+    n_rows = n_t if host_out is None else max(0, min(int(host_out.n_rows), n_t))
     out = None if host_out is not None else torch.empty(shape, dtype=dtype, device=eng.device)
     if n_k == 0:
         return out
     mean, entries = traj.prepare(groups, use_displacements)
-    kc = max(1, min(k_chunk, n_k, K_CHUNK_CAP))
+    kc = effective_k_chunk(k_chunk, n_k)
+    window = traj.window
     rows_alloc = 2 * kc
     ldp = (n_t + 3) // 4 * 4
     kv_dev = eng.upload_small(np.ascontiguousarray(k_vecs, np.float32))
@@ -375,7 +420,7 @@ def sed_on_device(traj: DeviceTrajectory, k_vecs: np.ndarray, groups: Sequence[O
     adig_bufs: Dict[int, torch.Tensor] = {}
     mode = _lib.MODE_COHERENT if complex_out else _lib.MODE_INCOHERENT
     if host_out is not None:
-        elem = (3 if complex_out else 1) * host_out.element_size()       # bytes per (f, k)
+        elem = 24 if complex_out else 4                                  # bytes per (f, k)
         chunk_bufs = [torch.empty((n_t, kc) + shape[2:], dtype=dtype, device=eng.device) for _ in range(2)]
         drained = [None, None]                                           # copy-stream events per buffer
         compute, copy = torch.cuda.current_stream(eng.device), eng.copy_stream
@@ -388,17 +433,17 @@ def sed_on_device(traj: DeviceTrajectory, k_vecs: np.ndarray, groups: Sequence[O
             eng.phase_digits(kv_dev[k0:k0 + nk], mean, idx_dev, n_sel, pitch, rows_alloc, out=adig)
             eng.project(adig, 2 * nk, rows_alloc, dig, expo, n_t, n_sel, pitch, P[g], ldp)
         if host_out is None:
-            eng.fft_sed(P, len(entries), group_stride, nk, n_t, ldp, mode, out, n_k, k0)
+            eng.fft_sed(P, len(entries), group_stride, nk, n_t, ldp, mode, out, n_k, k0, window)
             continue
         buf = chunk_bufs[ci & 1]
         if drained[ci & 1] is not None:
             compute.wait_event(drained[ci & 1])                          # its previous contents are on the host
-        eng.fft_sed(P, len(entries), group_stride, nk, n_t, ldp, mode, buf, kc, 0)
+        eng.fft_sed(P, len(entries), group_stride, nk, n_t, ldp, mode, buf, kc, 0, window)
         ready = torch.cuda.Event()
         ready.record(compute)
         copy.wait_event(ready)
-        _lib.call("psa_copy_rows", host_out.data_ptr() + k0 * elem, n_k * elem, buf.data_ptr(), kc * elem,
-                  nk * elem, n_rows, copy.cuda_stream)
+        _lib.call("psa_copy_rows", host_out.ptr + (host_out.k_offset + k0) * elem, host_out.n_k_total * elem,
+                  buf.data_ptr(), kc * elem, nk * elem, n_rows, copy.cuda_stream)
         drained[ci & 1] = torch.cuda.Event()
         drained[ci & 1].record(copy)
     if host_out is not None:

@@ -46,6 +46,13 @@ class SED:
         mag = np.abs(self.sed)
         return np.sum(mag * mag, axis=-1).astype(np.float32)
 
+    def __getstate__(self):
+        """Pickle / copy without the back-reference to the calculator (a weakref, and GPU state behind it)."""
+        state = dict(self.__dict__)
+        if state.get("context"):
+            state["context"] = {k: v for k, v in state["context"].items() if k != "calculator"}
+        return state
+
     # -- dict-style access for the README facade
     def keys(self) -> Iterator[str]:
         return (f.name for f in fields(self) if f.name != "context")

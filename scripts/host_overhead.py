@@ -7,7 +7,8 @@ from pathlib import Path
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
-from psa_b200 import SEDCalculator, synth  # noqa: E402
+from psa_b200 import SEDCalculator  # noqa: E402
+import synthetic as synth  # noqa: E402
 
 cfg = synth.baseline_config("c2")
 spec = cfg["spec"]

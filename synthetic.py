@@ -21,7 +21,7 @@ from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
-from .trajectory import Trajectory
+from psa_b200.trajectory import Trajectory
 
 BLOCK = 256  # frames per RNG block
 

@@ -14,6 +14,7 @@ GOLDEN = ROOT / "tests" / "golden"
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); skipped by -m 'not gpu'")
+    config.addinivalue_line("markers", "slow: minutes of host work (50 GB synthetic trajectory + CPU oracle)")
 
 
 @pytest.fixture(scope="session")

@@ -11,7 +11,8 @@ import numpy as np
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 
-from psa_b200 import SEDCalculator, synth  # noqa: E402
+from psa_b200 import SEDCalculator  # noqa: E402
+import synthetic as synth  # noqa: E402
 from psa_b200 import dist as pdist  # noqa: E402
 
 

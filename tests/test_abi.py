@@ -45,7 +45,7 @@ def test_bad_arguments_are_reported_not_crashed(lib):
     status = lib.psa_project(None, 0, 0, None, None, 0, 0, 0, None, 0, 0, None)
     assert status == _lib.ERR_BAD_ARG and b"psa_project" in lib.psa_last_error()
     with pytest.raises(ValueError):
-        _lib.check(lib.psa_digitize(None, None, None, 1, 1, 1, 64, None, None, None))
+        _lib.check(lib.psa_digitize(None, None, None, None, 1, 1, 1, 64, None, None, None))
     # strided row copy: empty extents are a no-op, a row wider than its pitch is refused
     assert lib.psa_copy_rows(None, 0, None, 0, 0, 0, None) == 0
     assert lib.psa_copy_rows(1, 8, 1, 16, 12, 4, None) == _lib.ERR_BAD_ARG and b"psa_copy_rows" in lib.psa_last_error()
@@ -71,15 +71,15 @@ def test_product_code_never_imports_the_oracle():
 def test_fft_planner_needs_no_gpu(lib):
     """Which frame counts take the mixed-radix core (no workspace) and which fall back to Bluestein is decided on
     the host: n = R * m with m = 4 * 2^a 3^b 5^c <= 4096 and R <= 256 is direct (R is a load-time split, so 28 =
-    7 * 4 qualifies), anything else needs the chirp scratch (8 bytes x 3 n_k x M, M = 2^s >= 2n-1)."""
+    7 * 4 qualifies), anything else needs the float64 chirp scratch (16 bytes x 3 n_k x M, M = 2^s >= 2n-1)."""
     direct = [4, 8, 12, 16, 20, 28, 48, 60, 1000, 1200, 3000, 4096, 10000, 12288, 16384, 20000, 50000, 65536, 2 ** 19]
     for n in direct:
         assert lib.psa_fft_workspace_bytes(n, 7, 2) == 0, n
         assert lib.psa_fft_plan_bytes(n) >= 16 * n, n
-    for n, m in ((2, 32), (7, 32), (250, 512), (3001, 8192), (8191, 16384), (4 * 2503, 32768), (10001, 32768)):
-        assert lib.psa_fft_workspace_bytes(n, 7, 2) == 2 * 7 * 3 * m * 8, n
+    for n, m in ((1, 32), (2, 32), (7, 32), (250, 512), (3001, 8192), (8191, 16384), (4 * 2503, 32768), (10001, 32768)):
+        assert lib.psa_fft_workspace_bytes(n, 7, 2) == 2 * 7 * 3 * m * 16, n
         assert lib.psa_fft_plan_bytes(n) >= 16 * (3 * m + n), n
-    for bad in (0, 1, 2 ** 19 + 1):
+    for bad in (0, -3, 2 ** 19 + 1):
         assert lib.psa_fft_plan_bytes(bad) == -1
 
 

@@ -124,3 +124,43 @@ def test_sliced_ingest_chain_and_exchange_over_gloo(world, n_t):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(all(r) for r in results), results
+
+
+# ------------------------------------------------------------------ shared host result (no funnel through one rank)
+def _shared_worker(rank, world, port, result_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_f, n_k = 6, 11
+        shared = pdist.SharedHostArray((n_f, n_k, 3), np.complex64, src=0, register=False)
+        k0, k1 = pdist.shard_range(n_k, rank, world)
+        full = (np.arange(n_f * n_k * 3).reshape(n_f, n_k, 3) * (1 + 2j)).astype(np.complex64)
+        shared.array[:, k0:k1] = full[:, k0:k1]                       # every rank fills its own column slice
+        dist.barrier()
+        ok = bool(np.array_equal(shared.array, full)) if rank == 0 else True
+        again = pdist.SharedHostArray((4,), np.float32, src=0, register=False)   # a second array, different shape
+        again.array[rank::world] = rank + 1
+        dist.barrier()
+        ok = ok and bool(np.array_equal(again.array, [(i % world) + 1 for i in range(4)]))
+        dist.barrier()
+        shared.close()
+        again.close()
+        result_q.put((ok,))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_shared_host_array_over_gloo(world):
+    """Every rank maps the same POSIX shared-memory array and writes its k-slice; the source rank sees all of it."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shared_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(all(r) for r in results), results

@@ -225,7 +225,8 @@ def test_npy_cache_roundtrip_matches_reference_loader(tmp_path, gold_si):
 
 def test_mode_validation_needs_no_gpu():
     """Argument errors surface before any device work (reference: sed_calculator.py:190-191)."""
-    from psa_b200 import SEDCalculator, synth
+    from psa_b200 import SEDCalculator
+    import synthetic as synth
     spec = synth.si_spec("tiny", n_cells=1, n_frames=8, seed=1)
     calc = SEDCalculator(spec.trajectory(threads=1), *spec.cells)
     mags, vecs = calc.get_k_path([1, 0, 0], 1.0, 3)
