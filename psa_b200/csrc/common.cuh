@@ -112,6 +112,12 @@ int launch_fft_plan(int64_t n_t, void* plan, cudaStream_t s);
 int launch_fft(const float* P, int64_t n_groups, int64_t group_stride, int64_t n_k, int64_t n_t, int64_t ldp,
                const void* plan, void* workspace, int64_t workspace_bytes, const float* window, int mode, void* out,
                int64_t n_k_total, int64_t k_offset, cudaStream_t s);
+// four-step kernel for long power-of-two columns (fft4.cu); coherent assembly only
+bool fft4_supported(int64_t n_t);
+int64_t fft4_workspace_bytes(int64_t n_t, int64_t n_k);
+int launch_fft4(const float* P, int64_t n_k, int64_t n_t, int64_t ldp, const void* plan, void* workspace,
+                int64_t workspace_bytes, const float* window, void* out, int64_t n_k_total, int64_t k_offset,
+                cudaStream_t s);
 int launch_chiral(const float2* z1, const float2* z2, int64_t n, int64_t stride1, int64_t stride2,
                   int opt, float* out, cudaStream_t s);
 int launch_intensity(const float2* sed, int64_t n_rows, int n_pol, float* out, cudaStream_t s);

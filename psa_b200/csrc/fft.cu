@@ -976,7 +976,9 @@ int fft_workspace_bytes(int64_t n_t, int64_t n_k, int64_t n_groups, int64_t* byt
   int64_t plan = 0;
   int st = fft_plan_bytes(n_t, &plan);
   if (st != PSA_OK) return st;
-  *bytes = direct_length(n_t) ? 0 : n_groups * n_k * 3 * bluestein_length(n_t) * (int64_t)sizeof(double2);
+  // 8192 / 16384 / 32768 frames: the four-step kernel's L2-resident intermediate + tile counters (coherent assembly)
+  if (fft4_supported(n_t)) *bytes = fft4_workspace_bytes(n_t, n_k);
+  else *bytes = direct_length(n_t) ? 0 : n_groups * n_k * 3 * bluestein_length(n_t) * (int64_t)sizeof(double2);
   return PSA_OK;
 }
 
@@ -995,7 +997,10 @@ int launch_fft(const float* P, int64_t n_groups, int64_t group_stride, int64_t n
   SedArgs a{P, (int)n_groups, group_stride, ldp, (int)n_t, out, n_k_total, k_offset, 1.0 / (double)n_t, window};
   const bool coherent = mode == PSA_MODE_COHERENT;
 
-  if (need == 0) {                                       // power of two: one fused kernel
+  if (coherent && fft4_supported(n_t))
+    return launch_fft4(P, n_k, n_t, ldp, plan_buf, workspace, workspace_bytes, window, out, n_k_total, k_offset, s);
+
+  if (need == 0 || direct_length(n_t)) {                 // mixed-radix lengths: one fused kernel
     FftGeom g = make_geom(n_t, plan);
     const size_t smem = smem_bytes(g, !coherent);
     // 3000 columns of 16384 points: 0.790 ms with direct 8-byte stores, 0.769 with pairs, 0.757 with clusters of 4

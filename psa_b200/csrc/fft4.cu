@@ -1,0 +1,270 @@
+// Four-step time FFT + coherent assembly for long power-of-two columns (n_t = 8192, 16384, 32768) - the
+// frame counts of every BASELINE config.  Replaces, for those lengths, the one-CTA-per-(column, residue)
+// kernel of fft.cu, whose 8-byte scattered result stores, 4x redundant column reads and ~190 instructions per
+// point held it at 13 % of the HBM roofline (profiles/r01g_ncu_full_c2.md).
+//
+// ONE persistent kernel runs both stages of the four-step scheme (fft4.cuh) as tiles of 4096 points handed out
+// through an atomic counter, in an order that software-pipelines the two stages over groups of 16 adjacent
+// (k, pol) columns:
+//
+//     phase p:   A-tiles of group p   (P -> 128-point transforms over n2 -> twiddle -> Y, float64)
+//                B-tiles of group p - LAG   (Y -> N1-point transforms over n1 -> / n_t -> result)
+//
+// Y lives in a ring of RING group slots (16 columns x n_t x 16 bytes each, 20-40 MB in total): it is written
+// and read back while still resident in the 126 MB L2, so HBM sees each input sample and each output value
+// once.  Per-group completion counters order the stages: a B-tile waits until the 16 columns of its group are
+// in Y, an A-tile that reuses a ring slot waits until the slot's previous group has been read.  Tiles are taken
+// in increasing order and a tile only ever waits for tiles with smaller numbers, which are running or done -
+// the grid needs no co-residency guarantee beyond "a CTA that took a tile is running".
+//
+// Stage B stores the reference's complex64 (n_f, n_k, 3) layout as 128-byte runs (16 columns of one frequency).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "fft4.cuh"
+
+namespace psa {
+namespace fft4 {
+
+__constant__ double2 c_w128[128];            // w_128^e
+
+struct Args {
+  const float* P;
+  int64_t ldp;
+  const float* window;
+  const double2* tw;          // w_n^e, e < n (start of the FFT plan)
+  double2* ybuf;              // RING slots of 16 columns x n
+  int* counter;               // next tile
+  int* done_a;                // [n_groups] stage-A tiles finished per group
+  int* done_b;                // [n_groups] stage-B tiles whose Y reads are finished
+  float2* out;                // already offset to column k_offset * 3
+  int64_t fstride;            // elements between consecutive frequencies of the result (n_k_total * 3)
+  int n_cols, n_groups, lag, ring, total_items;
+  double inv_n;
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void wait_count(const int* p, int want) {   // one thread spins; the CTA joins at the barrier after
+  while (ld_acquire(p) < want) __nanosleep(64);
+}
+
+struct LoadP {                 // one sample of a column of P, widened (and tapered) in float64
+  const float* re;
+  const float* im;
+  const float* win;
+  __device__ __forceinline__ c2 operator()(int t) const {
+    c2 v = mk((double)__ldcs(re + t), (double)__ldcs(im + t));       // read once: evict first, Y should own the L2
+    if (win != nullptr) {
+      const double w = (double)__ldg(win + t);
+      v.x *= w;
+      v.y *= w;
+    }
+    return v;
+  }
+};
+
+template <int N1>
+struct LoadY {                 // Y[c][k2_0 + k2l][n1] of the tile's group; L2 only (other SMs wrote it in this launch)
+  const double2* y_group;
+  int k2_0;
+  __device__ __forceinline__ c2 operator()(int tau, int n1) const {
+    const int c = tau & 15, k2l = tau >> 4;
+    const double2 v = __ldcg(y_group + ((int64_t)c * kN2 + k2_0 + k2l) * N1 + n1);
+    return mk(v.x, v.y);
+  }
+};
+
+template <int N1>
+struct StoreOut {
+  float2* out;                 // offset to the group's first column
+  int64_t fstride;
+  int k2_0, cols_live;
+  double inv_n;
+  __device__ __forceinline__ void operator()(int c, int k2l, int k1, c2 v) const {
+    if (c < cols_live)
+      __stcs(out + (int64_t)(k2_0 + k2l + kN2 * k1) * fstride + c, make_float2((float)(v.x * inv_n), (float)(v.y * inv_n)));
+  }
+};
+
+template <int N1>
+__global__ void __launch_bounds__(kThreads, 2) fft4_kernel(Args a) {
+  using G = Geo<N1>;
+  extern __shared__ double2 f4_smem[];
+  c2* exch = reinterpret_cast<c2*>(f4_smem);
+  c2* twb = exch + G::exchange_elems;                     // w_N1^(j s), rows of 17
+  __shared__ int s_item;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < G::q * 17; i += kThreads) {
+    const int j = i / 17, s = i % 17;
+    const double2 w = __ldg(a.tw + (s < 16 ? kN2 * j * s : 0));
+    twb[i] = mk(w.x, w.y);
+  }
+  const c2* w128 = reinterpret_cast<const c2*>(c_w128);
+  const c2* tw = reinterpret_cast<const c2*>(a.tw);
+  constexpr int TPG = G::tiles_per_group;
+
+  for (;;) {
+    __syncthreads();                                       // previous tile's shared-memory reads are finished
+    if (tid == 0) s_item = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= a.total_items) break;
+    const int phase = item / (2 * TPG), r = item % (2 * TPG);
+    if (r < TPG) {                                         // ---------------- stage A tile
+      const int g = phase;
+      if (g >= a.n_groups) continue;
+      const int c_local = r / G::a_tiles_per_column, n1_0 = (r % G::a_tiles_per_column) * kN1Tile;
+      const int col = g * kColsPerGroup + c_local;
+      if (g >= a.ring && tid == 0) wait_count(a.done_b + g - a.ring, TPG);     // the slot's previous group has been read
+      if (col < a.n_cols) {
+        const int k = col / 3, pol = col % 3;
+        LoadP load{a.P + ((int64_t)(2 * k) * 3 + pol) * a.ldp, a.P + ((int64_t)(2 * k + 1) * 3 + pol) * a.ldp, a.window};
+        // the loads do not depend on the ring slot: issue them before joining the wait
+        c2* y_col = reinterpret_cast<c2*>(a.ybuf) + ((int64_t)(g % a.ring) * kColsPerGroup + c_local) * G::n;
+        stage_a_pass1<N1>(tid, n1_0, load, w128, exch);
+        __syncthreads();                                   // exchange complete; tid 0 has seen the slot free
+        stage_a_pass2<N1>(tid, n1_0, exch, tw, y_col);
+        __threadfence();                                   // Y visible GPU-wide before the count goes up
+      }
+      __syncthreads();
+      if (tid == 0) atomicAdd(a.done_a + g, 1);
+    } else {                                               // ---------------- stage B tile
+      const int g = phase - a.lag;
+      if (g < 0 || g >= a.n_groups) continue;
+      const int k2_0 = (r - TPG) * G::k2_per_tile;
+      if (tid == 0) wait_count(a.done_a + g, TPG);         // all 16 columns of the group are in Y
+      __syncthreads();
+      LoadY<N1> load_y{a.ybuf + (int64_t)(g % a.ring) * kColsPerGroup * G::n, k2_0};
+      stage_b_pass1<N1>(tid, load_y, twb, exch);
+      __syncthreads();                                     // Y of this tile is in registers / shared memory
+      if (tid == 0) atomicAdd(a.done_b + g, 1);
+      StoreOut<N1> sink{a.out + (int64_t)g * kColsPerGroup, a.fstride, k2_0, min(kColsPerGroup, a.n_cols - g * kColsPerGroup),
+                        a.inv_n};
+      stage_b_pass2<N1>(tid, exch, sink);
+    }
+  }
+}
+
+static int n1_of(int64_t n_t) {
+  if (n_t == 8192) return 64;
+  if (n_t == 16384) return 128;
+  if (n_t == 32768) return 256;
+  return 0;
+}
+
+template <int N1>
+static size_t smem_bytes() { return (size_t)(Geo<N1>::exchange_elems + Geo<N1>::q * 17) * sizeof(double2); }
+
+struct Schedule {
+  int n_groups, lag, ring, resident;
+  int64_t ctl_bytes, y_bytes;
+};
+
+static Schedule make_schedule(int64_t n_t, int64_t n_cols, int sms) {
+  Schedule s;
+  const int n1 = n1_of(n_t), tpg = n1 / 2;
+  s.n_groups = (int)((n_cols + kColsPerGroup - 1) / kColsPerGroup);
+  s.resident = 2 * sms;
+  // Tile numbering: phase p = [A-tiles of group p | B-tiles of group p - lag].  Between the last A-tile of a group
+  // and its first B-tile lie lag * 2 tpg tiles; between the last B-tile of a group and the first A-tile that reuses
+  // its ring slot, (ring - lag - 1) * 2 tpg.  Both distances exceed the number of resident CTAs, so that a tile
+  // normally finds what it waits for already complete.
+  const int need = s.resident + tpg / 2;
+  s.lag = 1;
+  while (s.lag * 2 * tpg < need) ++s.lag;
+  s.ring = s.lag + 2;
+  while ((s.ring - s.lag - 1) * 2 * tpg < need) ++s.ring;
+  if (s.ring > s.n_groups) s.ring = s.n_groups > 0 ? s.n_groups : 1;     // never more slots than groups
+  s.ctl_bytes = round_up((int64_t)(1 + 2 * (int64_t)s.n_groups) * sizeof(int), 256);
+  s.y_bytes = (int64_t)s.ring * kColsPerGroup * n_t * sizeof(double2);
+  return s;
+}
+
+}  // namespace fft4
+
+bool fft4_supported(int64_t n_t) {
+  static const bool off = getenv("PSA_FFT4") != nullptr && atoi(getenv("PSA_FFT4")) == 0;
+  return !off && fft4::n1_of(n_t) != 0;
+}
+
+static int device_sms() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  else cudaGetLastError();
+  return sms > 0 ? sms : 148;
+}
+
+int64_t fft4_workspace_bytes(int64_t n_t, int64_t n_k) {
+  if (!fft4_supported(n_t) || n_k <= 0) return 0;
+  // sized for 148 SMs when no device is current (the planner is callable without a GPU)
+  const fft4::Schedule s = fft4::make_schedule(n_t, n_k * 3, device_sms());
+  return s.ctl_bytes + s.y_bytes;
+}
+
+template <int N1>
+static int launch_one(const fft4::Args& a, const fft4::Schedule& sch, cudaStream_t s) {
+  using namespace fft4;
+  const size_t smem = smem_bytes<N1>();
+  PSA_CUDA(cudaFuncSetAttribute(fft4_kernel<N1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t tiles = (int64_t)sch.n_groups * 2 * Geo<N1>::tiles_per_group;
+  const int grid = (int)(tiles < sch.resident ? tiles : sch.resident);
+  fft4_kernel<N1><<<grid, kThreads, smem, s>>>(a);
+  return launch_status("fft4_kernel");
+}
+
+// coherent assembly only: complex64 out[f][k_offset + k][pol]
+int launch_fft4(const float* P, int64_t n_k, int64_t n_t, int64_t ldp, const void* plan_buf, void* workspace,
+                int64_t workspace_bytes, const float* window, void* out, int64_t n_k_total, int64_t k_offset,
+                cudaStream_t s) {
+  using namespace fft4;
+  static bool w128_ready[64] = {};
+  int dev = 0;
+  PSA_CUDA(cudaGetDevice(&dev));
+  const Schedule sch = make_schedule(n_t, n_k * 3, device_sms());
+  PSA_REQUIRE(workspace != nullptr && workspace_bytes >= sch.ctl_bytes + sch.y_bytes,
+              "psa_fft_sed: workspace of %lld bytes required for n_t=%lld (got %lld)",
+              (long long)(sch.ctl_bytes + sch.y_bytes), (long long)n_t, (long long)workspace_bytes);
+  PSA_REQUIRE(((uintptr_t)workspace & 255) == 0, "psa_fft_sed: workspace must be 256-byte aligned");
+  if (dev < 64 && !w128_ready[dev]) {                       // per device; idempotent, so a race only repeats the copy
+    double2 host[128];
+    for (int e = 0; e < 128; ++e) {
+      const double ang = -2.0 * 3.14159265358979323846 * (double)e / 128.0;
+      host[e] = make_double2(cos(ang), sin(ang));
+    }
+    // exact values at the octants
+    host[0] = make_double2(1.0, 0.0); host[32] = make_double2(0.0, -1.0); host[64] = make_double2(-1.0, 0.0);
+    host[96] = make_double2(0.0, 1.0);
+    PSA_CUDA(cudaMemcpyToSymbolAsync(c_w128, host, sizeof(host), 0, cudaMemcpyHostToDevice, s));
+    PSA_CUDA(cudaStreamSynchronize(s));                    // `host` is on the stack
+    w128_ready[dev] = true;
+  }
+  PSA_CUDA(cudaMemsetAsync(workspace, 0, (size_t)sch.ctl_bytes, s));
+  Args a;
+  a.P = P;
+  a.ldp = ldp;
+  a.window = window;
+  a.tw = reinterpret_cast<const double2*>(plan_buf);
+  int* ctl = reinterpret_cast<int*>(workspace);
+  a.counter = ctl;
+  a.done_a = ctl + 1;
+  a.done_b = ctl + 1 + sch.n_groups;
+  a.ybuf = reinterpret_cast<double2*>(reinterpret_cast<char*>(workspace) + sch.ctl_bytes);
+  a.out = reinterpret_cast<float2*>(out) + k_offset * 3;
+  a.fstride = n_k_total * 3;
+  a.n_cols = (int)(n_k * 3);
+  a.n_groups = sch.n_groups;
+  a.lag = sch.lag;
+  a.ring = sch.ring;
+  const int n1 = n1_of(n_t);
+  a.total_items = (sch.n_groups + sch.lag) * 2 * (n1 / 2);
+  a.inv_n = 1.0 / (double)n_t;
+  if (n1 == 64) return launch_one<64>(a, sch, s);
+  if (n1 == 128) return launch_one<128>(a, sch, s);
+  return launch_one<256>(a, sch, s);
+}
+
+}  // namespace psa

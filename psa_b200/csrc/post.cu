@@ -106,70 +106,95 @@ __device__ __forceinline__ void ised_uv(const IsedBatch& b, int p, int g, double
   }
 }
 
+// One output value: the float32 running sum over the atom's groups, rescaled and added to the mean in the
+// reference's order of operations.
+struct IsedAtom {
+  float mean[3];
+  double U[3], V[3];          // single-group fast path
+  double ca, sa;
+  int m_begin, m_end;
+};
+
+__device__ __forceinline__ void ised_values(const IsedBatch& b, const IsedAtom& at, int p, double2 cs, float dv, float ml,
+                                            float (&val)[3], float& running_max) {
+  float w[3] = {0.f, 0.f, 0.f};
+  if (at.m_end - at.m_begin == 1) {                        // the usual case: disjoint groups
+#pragma unroll
+    for (int pol = 0; pol < 3; ++pol) w[pol] = (float)(cs.x * at.U[pol] + cs.y * at.V[pol]);
+#pragma unroll
+    for (int pol = 0; pol < 3; ++pol) running_max = fmaxf(running_max, fabsf(w[pol]));
+  } else {                                                 // overlapping groups: float32 running sum, group by group
+    for (int m = at.m_begin; m < at.m_end; ++m) {
+      double U[3], V[3];
+      ised_uv(b, p, __ldg(b.member_grp + m), at.ca, at.sa, U, V);
+#pragma unroll
+      for (int pol = 0; pol < 3; ++pol) {
+        w[pol] = (float)((double)w[pol] + (cs.x * U[pol] + cs.y * V[pol]));
+        running_max = fmaxf(running_max, fabsf(w[pol]));   // the reference's running maximum (after every group)
+      }
+    }
+  }
+#pragma unroll
+  for (int pol = 0; pol < 3; ++pol) val[pol] = __fadd_rn(at.mean[pol], __fmul_rn(__fdiv_rn(w[pol], dv), ml));
+}
+
 // kWrite = false: max over (frame, atom of a group, pol) of |running sum after that group| per point -> wmax[p]
 //                 (the 'auto' rescale's max_wiggle_amp_all, sed_calculator.py:502-504), nothing is stored;
 // kWrite = true : out[p][f][a][pol] = mean + ((sum / div[p]) * mul[p]) in float32, the reference's order of operations
 //                 (sed_calculator.py:517-533); div = mul = 1 leaves the sum untouched bit for bit.
-template <bool kWrite>
+// kWide: n_a % 4 == 0 - a warp's 32 atoms x 3 values of one frame (384 contiguous bytes of the output) are staged in
+// shared memory and leave as 24 aligned 16-byte stores (three full 128-byte lines per warp instead of 96 4-byte pieces).
+template <bool kWrite, bool kWide>
 __global__ void __launch_bounds__(128) ised_batch_kernel(IsedBatch b, const float* __restrict__ div,
                                                          const float* __restrict__ mul, float* __restrict__ out,
                                                          float* __restrict__ wmax) {
   __shared__ double2 phasor[kIsedMaxFrames];
+  __shared__ __align__(16) float stage[4][2][96];          // [warp][double buffer][32 atoms x 3]
   ised_fill_phasors(phasor, b.n_frames);
   __syncthreads();
-  const int p = blockIdx.y;
+  const int p = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t a_warp = a - lane;                         // first atom of this warp
+  const bool live = a < b.n_a;
   float local_max = 0.f;
-  if (a < b.n_a) {
-    const float m0 = __ldg(b.mean + a * 3), m1 = __ldg(b.mean + a * 3 + 1), m2 = __ldg(b.mean + a * 3 + 2);
-    const float xproj = __fmaf_rn(m2, __ldg(b.khat + 2), __fmaf_rn(m1, __ldg(b.khat + 1), __fmul_rn(m0, __ldg(b.khat))));
-    double sa, ca;
-    sincos((double)__fmul_rn(__ldg(b.k_act + p), xproj), &sa, &ca);
-    const int m_begin = __ldg(b.member_off + a), m_end = __ldg(b.member_off + a + 1);
-    const float mm[3] = {m0, m1, m2};
-    const float dv = kWrite ? __ldg(div + p) : 1.f, ml = kWrite ? __ldg(mul + p) : 1.f;
-    float* o = kWrite ? out + ((int64_t)p * b.n_frames * b.n_a + a) * 3 : nullptr;
-    if (m_end - m_begin == 1) {                              // the usual case: disjoint groups
-      double U[3], V[3];
-      ised_uv(b, p, __ldg(b.member_grp + m_begin), ca, sa, U, V);
-      for (int f = 0; f < b.n_frames; ++f) {
-        const double2 cs = phasor[f];
-#pragma unroll
-        for (int pol = 0; pol < 3; ++pol) {
-          const float w = (float)(cs.x * U[pol] + cs.y * V[pol]);
-          if (kWrite) o[(int64_t)f * b.n_a * 3 + pol] = __fadd_rn(mm[pol], __fmul_rn(__fdiv_rn(w, dv), ml));
-          else local_max = fmaxf(local_max, fabsf(w));
-        }
-      }
-    } else if (m_end == m_begin) {                           // not reconstructed: the mean position
-      if (kWrite)
-        for (int f = 0; f < b.n_frames; ++f)
-#pragma unroll
-          for (int pol = 0; pol < 3; ++pol)
-            o[(int64_t)f * b.n_a * 3 + pol] = __fadd_rn(mm[pol], __fmul_rn(__fdiv_rn(0.f, dv), ml));
-    } else {                                                 // overlapping groups: float32 running sum, group by group
-      for (int f = 0; f < b.n_frames; ++f) {
-        const double2 cs = phasor[f];
-        float w[3] = {0.f, 0.f, 0.f};
-        for (int m = m_begin; m < m_end; ++m) {
-          double U[3], V[3];
-          ised_uv(b, p, __ldg(b.member_grp + m), ca, sa, U, V);
-#pragma unroll
-          for (int pol = 0; pol < 3; ++pol) {
-            w[pol] = (float)((double)w[pol] + (cs.x * U[pol] + cs.y * V[pol]));
-            if (!kWrite) local_max = fmaxf(local_max, fabsf(w[pol]));   // the reference's running maximum
-          }
-        }
-        if (kWrite)
-#pragma unroll
-          for (int pol = 0; pol < 3; ++pol)
-            o[(int64_t)f * b.n_a * 3 + pol] = __fadd_rn(mm[pol], __fmul_rn(__fdiv_rn(w[pol], dv), ml));
-      }
+  IsedAtom at = {};
+  if (live) {
+    at.mean[0] = __ldg(b.mean + a * 3);
+    at.mean[1] = __ldg(b.mean + a * 3 + 1);
+    at.mean[2] = __ldg(b.mean + a * 3 + 2);
+    const float xproj = __fmaf_rn(at.mean[2], __ldg(b.khat + 2), __fmaf_rn(at.mean[1], __ldg(b.khat + 1),
+                                                                          __fmul_rn(at.mean[0], __ldg(b.khat))));
+    sincos((double)__fmul_rn(__ldg(b.k_act + p), xproj), &at.sa, &at.ca);
+    at.m_begin = __ldg(b.member_off + a);
+    at.m_end = __ldg(b.member_off + a + 1);
+    if (at.m_end - at.m_begin == 1) ised_uv(b, p, __ldg(b.member_grp + at.m_begin), at.ca, at.sa, at.U, at.V);
+  }
+  const float dv = kWrite ? __ldg(div + p) : 1.f, ml = kWrite ? __ldg(mul + p) : 1.f;
+  float* o = kWrite ? out + (int64_t)p * b.n_frames * b.n_a * 3 : nullptr;
+  const int n_warp = (int)min((int64_t)32, b.n_a - a_warp);                 // atoms of this warp that exist (<= 0: none)
+  for (int f = 0; f < b.n_frames; ++f) {
+    float val[3] = {0.f, 0.f, 0.f};
+    if (live) ised_values(b, at, p, phasor[f], dv, ml, val, local_max);
+    if (!kWrite) continue;
+    float* row = o + ((int64_t)f * b.n_a + a_warp) * 3;
+    if (kWide) {
+      float* st = stage[warp][f & 1];
+      st[lane * 3] = val[0];
+      st[lane * 3 + 1] = val[1];
+      st[lane * 3 + 2] = val[2];
+      __syncwarp();
+      if (lane * 4 < n_warp * 3)                                            // n_warp % 4 == 0 here: whole float4s only
+        reinterpret_cast<float4*>(row)[lane] = reinterpret_cast<const float4*>(st)[lane];
+      // the other buffer is written next; this one again two frames from now, after the next __syncwarp
+    } else if (live) {
+      row[lane * 3] = val[0];
+      row[lane * 3 + 1] = val[1];
+      row[lane * 3 + 2] = val[2];
     }
   }
   if (!kWrite) {
     for (int o2 = 16; o2 > 0; o2 >>= 1) local_max = fmaxf(local_max, __shfl_xor_sync(0xffffffffu, local_max, o2));
-    if ((threadIdx.x & 31) == 0 && local_max > 0.f) atomicMax(reinterpret_cast<int*>(wmax + p), __float_as_int(local_max));
+    if (lane == 0 && local_max > 0.f) atomicMax(reinterpret_cast<int*>(wmax + p), __float_as_int(local_max));
   }
 }
 
@@ -186,7 +211,7 @@ int launch_ised_absmax(const IsedBatch& b, float* wmax, cudaStream_t s) {
   PSA_CUDA(cudaMemsetAsync(wmax, 0, sizeof(float) * (size_t)(b.n_points > 0 ? b.n_points : 0), s));
   if (b.n_a == 0 || b.n_frames == 0 || b.n_points == 0) return PSA_OK;
   dim3 grid((unsigned)((b.n_a + 127) / 128), (unsigned)b.n_points);
-  ised_batch_kernel<false><<<grid, 128, 0, s>>>(b, nullptr, nullptr, nullptr, wmax);
+  ised_batch_kernel<false, false><<<grid, 128, 0, s>>>(b, nullptr, nullptr, nullptr, wmax);
   return launch_status("ised_batch_kernel<max>");
 }
 
@@ -195,7 +220,10 @@ int launch_ised_frames(const IsedBatch& b, const float* div, const float* mul, f
   if (st != PSA_OK) return st;
   if (b.n_a == 0 || b.n_frames == 0 || b.n_points == 0) return PSA_OK;
   dim3 grid((unsigned)((b.n_a + 127) / 128), (unsigned)b.n_points);
-  ised_batch_kernel<true><<<grid, 128, 0, s>>>(b, div, mul, out, nullptr);
+  if (b.n_a % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+    ised_batch_kernel<true, true><<<grid, 128, 0, s>>>(b, div, mul, out, nullptr);
+  else
+    ised_batch_kernel<true, false><<<grid, 128, 0, s>>>(b, div, mul, out, nullptr);
   return launch_status("ised_batch_kernel<write>");
 }
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Time psa_fft_sed alone (CUDA events) for one shape; used to pick the sub-transform length.
-    PSA_FFT_MAX_POINTS=4096 python scripts/fft_tune.py 16384 200
+"""Time psa_fft_sed alone (CUDA events) for one shape.
+    python scripts/fft_tune.py 16384 1024 [mode]        PSA_FFT4=0 selects the one-CTA-per-column kernel
 """
 import os
 import sys
@@ -21,12 +21,13 @@ for _ in range(3):
     eng.fft_sed(P, 1, P.numel(), n_k, n_t, n_t, mode, out, n_k, 0)
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+reps = 10
 a.record()
-for _ in range(10):
+for _ in range(reps):
     eng.fft_sed(P, 1, P.numel(), n_k, n_t, n_t, mode, out, n_k, 0)
 b.record()
 torch.cuda.synchronize()
-ms = a.elapsed_time(b) / 10
+ms = a.elapsed_time(b) / reps
 gbs = (48.0 if mode == 0 else 28.0) * n_k * n_t / ms / 1e6
-print(f"max_points={os.environ.get('PSA_FFT_MAX_POINTS', 'default')} n_t={n_t} n_k={n_k} mode={mode}: "
-      f"{ms:.3f} ms  {gbs:.0f} GB/s algorithmic")
+print(f"fft4={os.environ.get('PSA_FFT4', '1')} n_t={n_t} n_k={n_k} mode={mode}: {ms:.3f} ms  {gbs:.0f} GB/s algorithmic "
+      f"({gbs / 6548.8:.3f} of the measured HBM peak)")

@@ -72,13 +72,19 @@ def test_fft_planner_needs_no_gpu(lib):
     """Which frame counts take the mixed-radix core (no workspace) and which fall back to Bluestein is decided on
     the host: n = R * m with m = 4 * 2^a 3^b 5^c <= 4096 and R <= 256 is direct (R is a load-time split, so 28 =
     7 * 4 qualifies), anything else needs the float64 chirp scratch (16 bytes x 3 n_k x M, M = 2^s >= 2n-1)."""
-    direct = [4, 8, 12, 16, 20, 28, 48, 60, 1000, 1200, 3000, 4096, 10000, 12288, 16384, 20000, 50000, 65536, 2 ** 19]
+    direct = [4, 8, 12, 16, 20, 28, 48, 60, 1000, 1200, 3000, 4096, 10000, 12288, 20000, 50000, 65536, 2 ** 19]
     for n in direct:
         assert lib.psa_fft_workspace_bytes(n, 7, 2) == 0, n
         assert lib.psa_fft_plan_bytes(n) >= 16 * n, n
     for n, m in ((1, 32), (2, 32), (7, 32), (250, 512), (3001, 8192), (8191, 16384), (4 * 2503, 32768), (10001, 32768)):
         assert lib.psa_fft_workspace_bytes(n, 7, 2) == 2 * 7 * 3 * m * 16, n
         assert lib.psa_fft_plan_bytes(n) >= 16 * (3 * m + n), n
+    # 8192 / 16384 / 32768 frames take the four-step kernel: a ring of L2-resident float64 group slots
+    # (16 columns x n_t x 16 bytes each, a few tens of MB whatever the k count) + tile counters
+    for n in (8192, 16384, 32768):
+        ws = lib.psa_fft_workspace_bytes(n, 1000, 1)
+        assert 16 * n * 16 * 3 < ws < 64 << 20, (n, ws)
+        assert lib.psa_fft_workspace_bytes(n, 2, 1) <= 16 * n * 16 + 4096, n       # one group: one slot
     for bad in (0, -3, 2 ** 19 + 1):
         assert lib.psa_fft_plan_bytes(bad) == -1
 

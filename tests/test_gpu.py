@@ -278,8 +278,37 @@ def test_fft_rejects_unsupported_length(eng):
         eng.fft_plan(2 ** 19 + 1)
 
 
-def test_fft_window_is_applied_in_float64(eng):
-    n_t, n_k = 4096, 2
+@pytest.mark.parametrize("n_t,n_k,n_k_total,k_off", [(8192, 70, 70, 0), (16384, 54, 60, 5), (32768, 23, 23, 0),
+                                                     (16384, 1, 1, 0), (8192, 16, 16, 0)])
+def test_fft_four_step_many_columns(eng, n_t, n_k, n_k_total, k_off):
+    """The four-step kernel (8192 / 16384 / 32768 frames) on enough columns to wrap its ring of L2-resident group
+    slots several times, a ragged last group of columns, and a result wider than the call's k-range."""
+    rng = np.random.default_rng(n_t + n_k)
+    P = rng.standard_normal((2 * n_k, 3, n_t)).astype(np.float32)
+    t = np.arange(n_t)
+    P[0::2] += 40 * np.cos(2 * np.pi * 123 * t / n_t).astype(np.float32)       # a strong line over the noise floor
+    P[1::2] += 40 * np.sin(2 * np.pi * 123 * t / n_t).astype(np.float32)
+    out = torch.full((n_t, n_k_total, 3), float("nan"), dtype=torch.complex64, device=eng.device)
+    for _ in range(2):                                                           # second call reuses plan + workspace
+        eng.fft_sed(dev(eng, P), 1, P.size, n_k, n_t, n_t, 0, out, n_k_total, k_off)
+    got = out.cpu().numpy()
+    z = P[0::2].astype(np.float64) + 1j * P[1::2].astype(np.float64)
+    want = (np.fft.fft(z, axis=-1) / n_t).transpose(2, 0, 1)
+    # float64 transform, one float32 rounding: every bin is accurate relative to ITS OWN magnitude, like NumPy's
+    # complex64 FFT (which is the float64 transform rounded once)
+    sel = got[:, k_off:k_off + n_k, :]
+    assert np.abs(sel - want).max() < 1.5e-7 * np.abs(want).max()
+    weak = np.abs(want) > 1e-9 * np.abs(want).max()
+    assert (np.abs(sel - want)[weak] / np.abs(want)[weak]).max() < 2e-7
+    assert (sel == want.astype(np.complex64)).mean() > 0.999                     # = the float64 transform rounded once
+    untouched = np.ones(n_k_total, bool)
+    untouched[k_off:k_off + n_k] = False
+    assert np.isnan(got[:, untouched, :].real).all()
+
+
+@pytest.mark.parametrize("n_t", [4096, 8192])
+def test_fft_window_is_applied_in_float64(eng, n_t):
+    n_k = 2
     rng = np.random.default_rng(3)
     P = rng.standard_normal((2 * n_k, 3, n_t)).astype(np.float32)
     w = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(n_t) / n_t)).astype(np.float32)
@@ -295,7 +324,7 @@ def test_non_finite_samples_poison_their_frame(eng):
     value and every projection of that frame comes out NaN (the reference propagates non-finite input as well)."""
     from psa_b200 import _lib
     rng = np.random.default_rng(8)
-    n_t, n_a = 70, 128
+    n_t, n_a = 72, 128
     data = rng.standard_normal((n_t, n_a, 3)).astype(np.float32)
     data[5, 17, 1] = np.nan
     data[9, 3, 2] = np.inf

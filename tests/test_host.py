@@ -279,3 +279,21 @@ def test_lattice_and_k_grid_equal_the_real_reference_on_random_inputs(seed):
     assert got[2] == want[2] and got[0].dtype == want[0].dtype and got[1].dtype == want[1].dtype
     np.testing.assert_array_equal(got[0], want[0])
     np.testing.assert_array_equal(got[1], want[1])
+
+
+def test_four_step_fft_thread_code_on_the_host(tmp_path):
+    """psa_b200/csrc/fft4.cuh is plain C++ when compiled without nvcc: run both stages of the four-step FFT thread by
+    thread on the CPU (index maps, twiddles, butterflies) against a direct float64 transform, for the three lengths
+    the kernel serves.  Every output must be written exactly once."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+    gxx = shutil.which("g++")
+    if gxx is None:
+        import pytest
+        pytest.skip("g++ not available")
+    src = Path(__file__).resolve().parent / "fft4_host_check.cpp"
+    exe = tmp_path / "fft4_host_check"
+    subprocess.run([gxx, "-O2", "-std=c++17", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
