@@ -172,6 +172,18 @@ int psa_gather_bins(const float* sed, int64_t n_k, const int32_t* w_idx, const i
 int psa_disp_moments(const float* pos, const float* mean, const int32_t* idx, int64_t n_t, int64_t n_a,
                      int64_t n_sel, double* out2, void* stream);
 
+/* Device-side consumers of an intensity map, float32 [n] on the device (what the reference's plotter / GUI do on
+ * the host with the whole array: sed_plotter.py:160-181, 211-215; psa_gui.py:2424-2441):
+ *   psa_scale_intensity: in place; mode 0 linear, 1 log10(max(x, 1e-12)), 2 sqrt(max(x, 0)), 3 "dsqrt" sqrt(sqrt(max(x, 0)))
+ *   psa_minmax: out3 (device, 16 bytes) = [key(nanmin) u32][key(nanmax) u32][number of finite values u64], where
+ *               key(v) = bits(v) ^ (v < 0 ? 0xFFFFFFFF : 0x80000000) orders like the floats
+ *   psa_select_pass: one byte of a most-significant-first radix select over the finite values - hist[j][b] counts
+ *               the values whose key shares the top `done_bits` (0/8/16/24) bits of prefix[j] and whose next byte
+ *               is b, for m <= 4 searches at once; four passes yield exact order statistics (np.percentile's inputs) */
+int psa_scale_intensity(float* x, int64_t n, int mode, void* stream);
+int psa_minmax(const float* x, int64_t n, void* out3, void* stream);
+int psa_select_pass(const float* x, int64_t n, int done_bits, const uint32_t* prefix, int m, uint32_t* hist, void* stream);
+
 /* max |x| over n float32 values (device scalar out). */
 int psa_absmax(const float* x, int64_t n, float* out, void* stream);
 
@@ -180,6 +192,13 @@ int psa_absmax(const float* x, int64_t n, float* out, void* stream);
  * full_sed_data[:, k0:k1, :] (reference: sed_calculator.py:310, 325) while the next chunk is computed. */
 int psa_copy_rows(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width, int64_t height,
                   void* stream);
+
+/* LAMMPS text dump of iSED frames, byte for byte what the reference's out_to_qdump writes (reference:
+ * src/psa/io/writer.py:139-228; parsed back by src/psa/gui/psa_gui.py:1396-1455).  HOST pointers; frames are formatted
+ * by `n_threads` threads (0 = all cores) and written in order.
+ *   frames_host [n_frames][n_atoms][3] float32   types_host [n_atoms] int32   box9_host: the 3x3 box matrix, float32 */
+int psa_write_dump(const char* path, const float* frames_host, const int32_t* types_host, int64_t n_frames,
+                   int64_t n_atoms, const float* box9_host, int n_threads);
 
 /* Page-lock / release caller-owned host memory so that psa_copy_rows can stream into it asynchronously.  Used for a
  * result array in POSIX shared memory that every rank of a box maps: each rank copies its k-slice of

@@ -51,12 +51,16 @@ _SIGNATURES = {
     "psa_gather_bins": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "psa_disp_moments": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "psa_absmax": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "psa_scale_intensity": (c_int, [c_void_p, c_int64, c_int, c_void_p]),
+    "psa_minmax": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "psa_select_pass": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "psa_mean_accumulate": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "psa_digitize_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p,
                                   c_void_p, c_int64, c_int64, c_void_p]),
     "psa_copy_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "psa_digitize_rows_peers": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p,
                                         c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "psa_write_dump": (c_int, [c_char_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int]),
     "psa_host_register": (c_int, [c_void_p, c_int64]),
     "psa_host_unregister": (c_int, [c_void_p]),
     "psa_ipc_export": (c_int, [c_void_p, c_void_p, c_void_p]),

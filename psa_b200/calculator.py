@@ -208,13 +208,21 @@ class SEDCalculator:
     def calculate_intensity(self, k_points_mags: np.ndarray, k_vectors_3d: np.ndarray, basis_atom_indices=None,
                             basis_atom_types=None, summation_mode: str = "coherent",
                             k_grid_shape: Optional[Tuple[int, int]] = None, k_chunk_size: int = 500,
-                            max_freq: Optional[float] = None) -> SED:
+                            max_freq: Optional[float] = None, intensity_scale: str = "linear",
+                            vmin_percentile: Optional[float] = None, vmax_percentile: Optional[float] = None,
+                            global_range: bool = False) -> SED:
         """The heat-map the plotter and the GUI reduce a result to (reference: sed_plotter.py:127-130,
         psa_gui.py:2196-2214, 2424-2441), produced on the device: ``sum_pol |S|^2`` as float32
         ``(n_f, n_k)`` - for a coherent selection it comes straight out of the FFT kernel's |.|^2 epilogue,
         the complex spectra are never stored - cropped to ``0 <= f <= max_freq`` when given.  Only that
         array crosses PCIe (C4: 0.16 GB instead of 3.9 GB).  ``is_complex`` is False; ``freqs`` matches
-        the rows."""
+        the rows.
+
+        ``intensity_scale`` ('linear' | 'log' | 'sqrt' | 'dsqrt', reference: sed_plotter.py:160-181), the percentile
+        colour limits (``np.percentile`` of the finite values, sed_plotter.py:211-215) and ``global_range`` (``nanmin`` /
+        ``nanmax`` over every slice, psa_gui.py:2424-2441) are evaluated on the device as well; they land in
+        ``result.context['stats']`` (``vmin``, ``vmax``, ``global_min``, ``global_max``)."""
+        from . import consumers
         if summation_mode not in ("coherent", "incoherent"):
             raise ValueError(f"summation_mode must be 'coherent' or 'incoherent', got {summation_mode}")
         n_t = self.traj.n_frames
@@ -228,8 +236,20 @@ class SEDCalculator:
         _, proj_groups = grp.plan_sed_groups(groups, summation_mode)
         k_vecs = np.ascontiguousarray(np.asarray(k_vectors_3d, dtype=np.float32).reshape(-1, 3))
         k_chunk, n_k = max(1, int(k_chunk_size)), k_vecs.shape[0]
+        if str(intensity_scale).lower() not in consumers.SCALE_MODES:
+            raise ValueError(f"intensity scale must be one of {sorted(consumers.SCALE_MODES)}, got {intensity_scale!r}")
+        on_device = (str(intensity_scale).lower() != "linear" or vmin_percentile is not None
+                     or vmax_percentile is not None or global_range)
+        stats = None
         with torch.cuda.device(self.engine.device):
-            if n_k > effective_k_chunk(k_chunk, n_k):
+            if on_device:                                   # the whole (cropped) map stays on the device for the reductions
+                out = sed_on_device(self.device_trajectory, k_vecs, proj_groups, False, self.use_displacements,
+                                    k_chunk=k_chunk)
+                crop = out[:n_rows]
+                consumers.scale_intensity(self.engine, crop, intensity_scale)
+                stats = consumers.intensity_stats(self.engine, crop, vmin_percentile, vmax_percentile)
+                inten = self._to_host(crop)
+            elif n_k > effective_k_chunk(k_chunk, n_k):
                 host = torch.empty((n_rows, n_k), dtype=torch.float32, pin_memory=True)
                 sed_on_device(self.device_trajectory, k_vecs, proj_groups, False, self.use_displacements,
                               k_chunk=k_chunk, host_out=HostTarget(host.data_ptr(), n_k, 0, n_rows, host))
@@ -239,8 +259,12 @@ class SEDCalculator:
                 out = sed_on_device(self.device_trajectory, k_vecs, proj_groups, False, self.use_displacements,
                                     k_chunk=k_chunk)
                 inten = self._to_host(out[:n_rows])
+        ctx = self._context(groups)
+        if stats is not None:
+            ctx["stats"] = stats
+            ctx["intensity_scale"] = str(intensity_scale).lower()
         return SED(inten, freqs[:n_rows], k_points_mags, k_vectors_3d, k_grid_shape=k_grid_shape,
-                   is_complex=False, phase=None, context=self._context(groups))
+                   is_complex=False, phase=None, context=ctx)
 
     def _to_host(self, dev: torch.Tensor) -> np.ndarray:
         host = torch.empty(dev.shape, dtype=dev.dtype, pin_memory=True)

@@ -291,6 +291,24 @@ int psa_disp_moments(const float* pos, const float* mean, const int32_t* idx, in
   return launch_disp_moments(pos, mean, idx, n_t, n_a, n_sel, out2, as_stream(stream));
 }
 
+int psa_scale_intensity(float* x, int64_t n, int mode, void* stream) {
+  PSA_REQUIRE(n >= 0 && (n == 0 || x), "psa_scale_intensity: bad arguments");
+  DeviceGuard guard(x);
+  return launch_scale_intensity(x, n, mode, as_stream(stream));
+}
+
+int psa_minmax(const float* x, int64_t n, void* out3, void* stream) {
+  PSA_REQUIRE(n >= 0 && out3 && (n == 0 || x), "psa_minmax: bad arguments");
+  DeviceGuard guard(out3);
+  return launch_minmax(x, n, out3, as_stream(stream));
+}
+
+int psa_select_pass(const float* x, int64_t n, int done_bits, const uint32_t* prefix, int m, uint32_t* hist, void* stream) {
+  PSA_REQUIRE(n >= 0 && prefix && hist && (n == 0 || x), "psa_select_pass: bad arguments");
+  DeviceGuard guard(hist);
+  return launch_select_pass(x, n, done_bits, prefix, m, hist, as_stream(stream));
+}
+
 int psa_absmax(const float* x, int64_t n, float* out, void* stream) {
   PSA_REQUIRE(out && (n == 0 || x), "psa_absmax: null pointer");
   DeviceGuard guard(out);

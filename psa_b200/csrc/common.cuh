@@ -136,6 +136,10 @@ int launch_ised_absmax(const IsedBatch& b, float* wmax, cudaStream_t s);
 int launch_ised_frames(const IsedBatch& b, const float* div, const float* mul, float* out, cudaStream_t s);
 int launch_gather_bins(const float2* sed, int64_t n_k, const int32_t* w_idx, const int32_t* k_idx, int n_points,
                        int64_t out_stride, float2* out, cudaStream_t s);
+int launch_scale_intensity(float* x, int64_t n, int mode, cudaStream_t s);
+int launch_minmax(const float* x, int64_t n, void* out3, cudaStream_t s);
+int launch_select_pass(const float* x, int64_t n, int done_bits, const uint32_t* prefix, int m, unsigned int* hist,
+                       cudaStream_t s);
 int launch_disp_moments(const float* pos, const float* mean, const int32_t* idx, int64_t n_t, int64_t n_a,
                         int64_t n_sel, double* out2, cudaStream_t s);
 int launch_absmax(const float* x, int64_t n, float* out, cudaStream_t s);

@@ -245,6 +245,116 @@ int launch_gather_bins(const float2* sed, int64_t n_k, const int32_t* w_idx, con
 }
 
 // ---------------------------------------------------------------------------------------------
+// Device-side consumers of an intensity map (N3 of SURVEY.md 8f): what the reference's plotter and GUI compute on
+// the host from the full (n_f, n_k) array - intensity scaling (sed_plotter.py:160-181, psa_gui.py:_apply_intensity_
+// scaling), the global colour range (psa_gui.py:2424-2441: nanmin / nanmax) and percentile limits
+// (sed_plotter.py:211-215: np.percentile over the finite values) - so that only a heat map, or only two numbers,
+// cross PCIe.
+// ---------------------------------------------------------------------------------------------
+// mode 0 linear, 1 log10(max(x, 1e-12)), 2 sqrt(max(x, 0)), 3 sqrt(sqrt(max(x, 0)))   (float32, in place)
+__global__ void scale_intensity_kernel(float* __restrict__ x, int64_t n, int mode) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = x[i];
+    if (mode == 1) v = log10f(fmaxf(v, 1e-12f));
+    else if (mode == 2) v = sqrtf(fmaxf(v, 0.f));
+    else if (mode == 3) v = sqrtf(sqrtf(fmaxf(v, 0.f)));
+    x[i] = v;
+  }
+}
+
+int launch_scale_intensity(float* x, int64_t n, int mode, cudaStream_t s) {
+  PSA_REQUIRE(mode >= 0 && mode <= 3, "psa_scale_intensity: mode must be 0 (linear), 1 (log), 2 (sqrt) or 3 (dsqrt)");
+  if (n == 0 || mode == 0) return PSA_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  scale_intensity_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, n, mode);
+  return launch_status("scale_intensity_kernel");
+}
+
+// order-preserving key of a float32: unsigned comparison of keys == numeric comparison of the floats
+__device__ __forceinline__ uint32_t float_key(float v) {
+  const uint32_t b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ bool is_finite_bits(float v) { return (__float_as_uint(v) & 0x7f800000u) != 0x7f800000u; }
+
+// out[0] = min, out[1] = max over the non-NaN values (np.nanmin / np.nanmax), as float keys; out[2] = finite count
+__global__ void minmax_kernel(const float* __restrict__ x, int64_t n, unsigned int* __restrict__ key_min,
+                              unsigned int* __restrict__ key_max, unsigned long long* __restrict__ n_finite) {
+  uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+  unsigned long long cnt = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = __ldg(x + i);
+    if (v == v) {                                   // not NaN
+      const uint32_t k = float_key(v);
+      lo = min(lo, k);
+      hi = max(hi, k);
+    }
+    cnt += is_finite_bits(v) ? 1u : 0u;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(key_min, lo);
+    atomicMax(key_max, hi);
+    atomicAdd(n_finite, cnt);
+  }
+}
+
+// One pass of a most-significant-byte-first radix select over the FINITE values of x: for each of `m` searches,
+// hist[j][b] = number of values whose key agrees with prefix[j] on its top `done_bits` bits and whose next byte is b.
+__global__ void select_pass_kernel(const float* __restrict__ x, int64_t n, int done_bits, const uint32_t* __restrict__ prefix,
+                                   int m, unsigned int* __restrict__ hist) {
+  __shared__ unsigned int s_hist[4][256];
+  for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+  __syncthreads();
+  uint32_t pre[4];
+  for (int j = 0; j < 4; ++j) pre[j] = j < m ? __ldg(prefix + j) : 0u;
+  const uint32_t mask = done_bits == 0 ? 0u : 0xFFFFFFFFu << (32 - done_bits);
+  const int shift = 24 - done_bits;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = __ldg(x + i);
+    if (!is_finite_bits(v)) continue;
+    const uint32_t k = float_key(v);
+    for (int j = 0; j < m; ++j)
+      if ((k & mask) == (pre[j] & mask)) atomicAdd(&s_hist[j][(k >> shift) & 0xFF], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < m * 256; i += blockDim.x) {
+    const unsigned int c = (&s_hist[0][0])[i];
+    if (c) atomicAdd(hist + i, c);
+  }
+}
+
+int launch_minmax(const float* x, int64_t n, void* out3, cudaStream_t s) {
+  // out3: [key_min u32][key_max u32][n_finite u64]
+  unsigned int init[4] = {0xFFFFFFFFu, 0u, 0u, 0u};
+  PSA_CUDA(cudaMemcpyAsync(out3, init, sizeof(init), cudaMemcpyHostToDevice, s));
+  PSA_CUDA(cudaStreamSynchronize(s));                       // `init` is on the stack
+  if (n == 0) return PSA_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  unsigned int* u = reinterpret_cast<unsigned int*>(out3);
+  minmax_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, n, u, u + 1, reinterpret_cast<unsigned long long*>(u + 2));
+  return launch_status("minmax_kernel");
+}
+
+int launch_select_pass(const float* x, int64_t n, int done_bits, const uint32_t* prefix, int m, unsigned int* hist,
+                       cudaStream_t s) {
+  PSA_REQUIRE(m >= 1 && m <= 4, "psa_select_pass: 1 to 4 simultaneous searches");
+  PSA_REQUIRE(done_bits == 0 || done_bits == 8 || done_bits == 16 || done_bits == 24, "psa_select_pass: done_bits must be 0, 8, 16 or 24");
+  PSA_CUDA(cudaMemsetAsync(hist, 0, sizeof(unsigned int) * 256 * (size_t)m, s));
+  if (n == 0) return PSA_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  select_pass_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, n, done_bits, prefix, m, hist);
+  return launch_status("select_pass_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
 // Reductions
 // ---------------------------------------------------------------------------------------------
 __global__ void disp_moments_kernel(const float* __restrict__ pos, const float* __restrict__ mean,

@@ -508,6 +508,82 @@ def test_intensity_map_on_device(gold_si):
     np.testing.assert_array_equal(inc_map.sed, inc.sed)
 
 
+def test_device_side_consumers_match_numpy(eng, gold_si):
+    """N3: intensity scaling, nan-aware global range and np.percentile limits computed on the device."""
+    from psa_b200 import consumers
+    rng = np.random.default_rng(23)
+    x = (rng.standard_normal(200_003) ** 2 * 10.0 ** rng.integers(-9, 3, 200_003)).astype(np.float32)
+    x[::1000] = np.nan
+    x[5::5000] = np.inf
+    x[7] = -np.inf
+    x[11:20] = 0.0
+    x[30:33] = -2.5
+    d = dev(eng, x)
+    lo, hi, n = consumers.nan_range(eng, d)
+    assert lo == np.nanmin(x) and hi == np.nanmax(x) and n == int(np.isfinite(x).sum())
+    valid = x[np.isfinite(x)]
+    for qs in ((1.0, 99.0), (0.0, 100.0), (50.0,), (33.3, 99.99)):
+        got = consumers.percentiles(eng, d, qs)
+        want = [float(np.percentile(valid, q)) for q in qs]
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=0)
+    ranks = [0, 1, len(valid) // 2, len(valid) - 1]
+    np.testing.assert_array_equal(consumers.order_statistics(eng, d, ranks), np.sort(valid)[ranks])
+    pos = np.abs(rng.standard_normal(5000)).astype(np.float32)
+    pos[3] = 0.0
+    for name, fn in (("log", lambda a: np.log10(np.maximum(a, 1e-12))), ("sqrt", lambda a: np.sqrt(np.maximum(a, 0))),
+                     ("dsqrt", lambda a: np.sqrt(np.sqrt(np.maximum(a, 0)))), ("linear", lambda a: a)):
+        t = dev(eng, pos)
+        consumers.scale_intensity(eng, t, name)
+        np.testing.assert_allclose(t.cpu().numpy(), fn(pos), rtol=3e-7, atol=1e-7)
+    # through the calculator: the GUI's globally scaled k-path heat map
+    calc = _calc(gold_si)
+    kv = gold_si["kpath_110_vecs"]
+    lin = calc.calculate_intensity(np.zeros(len(kv)), kv)
+    res = calc.calculate_intensity(np.zeros(len(kv)), kv, intensity_scale="dsqrt", vmin_percentile=1.0,
+                                   vmax_percentile=99.0, global_range=True)
+    want = np.sqrt(np.sqrt(np.maximum(lin.sed, 0)))
+    np.testing.assert_allclose(res.sed, want, rtol=3e-7)
+    st = res.context["stats"]
+    np.testing.assert_allclose([st["global_min"], st["global_max"]], [res.sed.min(), res.sed.max()], rtol=0)
+    np.testing.assert_allclose([st["vmin"], st["vmax"]], np.percentile(res.sed, [1.0, 99.0]), rtol=1e-6)
+
+
+def test_cli_batch_driver(gold_si, tmp_path):
+    """N4: the YAML-driven batch run writes the reference's SED bundles, computes every direction once and reduces the
+    global maximum on the device; a second run loads the bundles back instead of recomputing."""
+    import json
+    import yaml
+    from psa_b200 import SED, cache, cli
+    calc = _calc(gold_si)
+    traj_file = tmp_path / "run.lammpstrj"
+    cache.save_npy_cache(calc.traj, traj_file)
+    cfg = {"md_system": {"dt": float(gold_si["dt_ps"]), "nx": 2, "ny": 2, "nz": 2, "lattice_parameter": synth.SI_A},
+           "sed_calculation": {"directions": ["x", [1, 1, 0]], "n_kpoints": 9, "bz_coverage": 1.0},
+           "ised": {"apply": True, "k_path": {"direction": "x", "n_points": 9, "bz_coverage": 1.0},
+                    "target_point": {"k_value": float(gold_si["ised_k_target"]), "w_value_thz": float(gold_si["ised_w_target"])},
+                    "reconstruction": {"rescaling_factor": 0.5, "num_animation_timesteps": 8}}}
+    (tmp_path / "cfg.yaml").write_text(yaml.safe_dump(cfg))
+    out = tmp_path / "out"
+    argv = ["--trajectory", str(traj_file), "--config", str(tmp_path / "cfg.yaml"), "--output-dir", str(out)]
+    assert cli.main(argv) == 0
+    got = SED.load(out / "sed_data_regular_x")
+    ref = gold_si["sed_coh_all_100"]
+    assert got.sed.shape == ref.shape and np.abs(got.sed - ref).max() < 2e-6 * np.abs(ref).max()
+    np.testing.assert_array_equal(got.k_vectors, gold_si["kpath_100_vecs"])
+    summary = json.loads((out / "summary.json").read_text())
+    peaks = [float(np.max(SED.load(out / f"sed_data_regular_{lbl}").intensity)) for lbl in ("x", "1.00_1.00_0.00")]
+    np.testing.assert_allclose([d["max_intensity"] for d in summary["directions"]], peaks, rtol=1e-5)
+    np.testing.assert_allclose(summary["global_max_intensity"], max(peaks), rtol=1e-5)
+    dump = (out / "ised_motion.dump").read_text().splitlines()
+    assert dump[0] == "ITEM: TIMESTEP" and len(dump) == 8 * (9 + len(gold_si["types"]))
+    assert cli.main(argv) == 0                                             # second run: loaded, not recomputed
+    again = json.loads((out / "summary.json").read_text())
+    assert all(d["loaded_from_cache"] for d in again["directions"])
+    assert cli.main(argv + ["--chiral", "--output-dir", str(tmp_path / "chi")]) == 0
+    chi = SED.load(tmp_path / "chi" / "sed_data_chiral_x")
+    assert chi.phase is not None and chi.phase.shape == ref.shape[:2]
+
+
 def test_chiral_sed_facade(gold_gr):
     calc = _calc(gold_gr)
     res = calc.calculate_chiral_sed([1, 0, 0], bz_coverage=4.0, n_k=10, chiral_axis="z")

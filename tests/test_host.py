@@ -297,3 +297,58 @@ def test_four_step_fft_thread_code_on_the_host(tmp_path):
     subprocess.run([gxx, "-O2", "-std=c++17", "-o", str(exe), str(src)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
+
+
+def test_dump_writer_formats_every_float32_like_python(tmp_path):
+    """The C++ writer's integer `%.6f` against CPython's own formatting of the same float32 values: exact ties of the
+    binary value (x.xxxxxx5 with a finite binary expansion), negatives that round to -0.000000, denormals, large
+    magnitudes (C library path), NaN and infinities, random values over 60 orders of magnitude."""
+    import numpy as np
+    from psa_b200.dump import write_lammps_dump
+    rng = np.random.default_rng(17)
+    special = np.array([0.0, -0.0, 0.5e-6, -0.5e-6, 1.5e-6, 2.5e-6, 0.0000005, 0.0000015, 0.125, 0.0078125, 1.0000005,
+                        -1e-7, -4.9e-7, 1e-45, -1e-45, 1e-38, 123456.7890625, 999999.9999995, 1048576.5, 8388607.5,
+                        16777216.0, 1.0995116e12, 3.4e38, -3.4e38, np.nan, np.inf, -np.inf, 0.9999995, 0.99999951,
+                        2.0 ** -20, 2.0 ** -21, 3 * 2.0 ** -21, 5 * 2.0 ** -22, 7.0000005, 43.4300005], np.float32)
+    rand = (rng.standard_normal(4000) * 10.0 ** rng.integers(-30, 30, 4000)).astype(np.float32)
+    vals = np.concatenate([special, rand, rng.uniform(-50, 50, 3000).astype(np.float32)])
+    vals = np.concatenate([vals, np.zeros((-len(vals)) % 3, np.float32)])
+    frames = vals.reshape(1, -1, 3)
+    n_at = frames.shape[1]
+    types = (np.arange(n_at) % 3 + 1).astype(np.int32)
+    box = np.array([[10.5, 0.0, 0.0], [0.0, 11.25, 0.0], [0.0, 0.0, 12.0]], np.float32)
+    out = tmp_path / "f.dump"
+    write_lammps_dump(str(out), frames, types, box, threads=3)
+    lines = out.read_text().splitlines()
+    assert lines[:9] == ["ITEM: TIMESTEP", "0", "ITEM: NUMBER OF ATOMS", str(n_at), "ITEM: BOX BOUNDS pp pp pp",
+                         "0.00000000 10.50000000", "0.00000000 11.25000000", "0.00000000 12.00000000",
+                         "ITEM: ATOMS id type x y z"]
+    for a, line in enumerate(lines[9:]):
+        x, y, z = (float(v) for v in frames[0, a])
+        assert line == f"{a + 1} {int(types[a])} {x:.6f} {y:.6f} {z:.6f}", (a, line)
+    # many frames, more frames than threads and fewer: same bytes whatever the thread count
+    many = rng.standard_normal((7, 33, 3)).astype(np.float32)
+    write_lammps_dump(str(tmp_path / "a.dump"), many, np.ones(33, int), box, threads=1)
+    write_lammps_dump(str(tmp_path / "b.dump"), many, np.ones(33, int), box, threads=16)
+    assert (tmp_path / "a.dump").read_bytes() == (tmp_path / "b.dump").read_bytes()
+
+
+def test_cli_host_logic(tmp_path):
+    """N4: config merge, direction labels, basis resolution and the missing-cache error of the batch driver
+    (reference: src/psa/cli.py:38-56, 79-89, 108-119)."""
+    import numpy as np
+    import pytest
+    from psa_b200 import cli
+    cfg = cli.update_dict_recursively({"a": {"b": 1, "c": 2}, "d": 3}, {"a": {"b": 5}, "e": {"f": 1}})
+    assert cfg == {"a": {"b": 5, "c": 2}, "d": 3, "e": {"f": 1}}
+    assert cli.direction_label([1, 0, 0], 1) == "1.00_0.00_0.00" and cli.direction_label(45, 2) == "45.0deg"
+    assert cli.direction_label("x y/z", 3) == "x_y-z" and cli.direction_label({"h": 1, "k": 1}, 4) == "h1_k1_l0"
+    types = np.array([1, 1, 2, 2, 3])
+    idx, sfx = cli.resolve_basis(types, 5, {"atom_indices": None, "atom_types": [2, 3]})
+    assert idx.tolist() == [2, 3, 4] and sfx == "_typebasis2_3"
+    idx, sfx = cli.resolve_basis(types, 5, {"atom_indices": [0, 4], "atom_types": [2]})
+    assert idx.tolist() == [0, 4] and sfx == "_idxbasis"
+    assert cli.resolve_basis(types, 5, {"atom_indices": None, "atom_types": [9]}) == (None, "")
+    with pytest.raises(ValueError):
+        cli.resolve_basis(types, 5, {"atom_indices": [7], "atom_types": None})
+    assert cli.main(["--trajectory", str(tmp_path / "none.lammpstrj"), "--output-dir", str(tmp_path / "o")]) == 1
