@@ -68,24 +68,28 @@ def order_statistics(eng, x: torch.Tensor, ranks: Sequence[int]) -> List[np.floa
 
 def percentiles(eng, x: torch.Tensor, qs: Sequence[float]) -> List[float]:
     """``np.percentile(x[isfinite(x)], q)`` (linear interpolation) for up to two percentiles, from exact order
-    statistics found on the device.  Returns NaN when there is no finite value."""
+    statistics found on the device, bit for bit: NumPy evaluates the quantile position of a float32 array in
+    float32 (``q / float32(100)``, ``(n - 1) * q``), so the interpolation weight is quantised - mirrored here, as is
+    its two-sided ``_lerp``.  Returns NaN when there is no finite value."""
     _, _, n = nan_range(eng, x)
     if n == 0:
         return [float("nan")] * len(qs)
     ranks, plan = [], []
     for q in qs:
-        pos = float(q) / 100.0 * (n - 1)
-        lo = int(np.floor(pos))
+        virt = (n - 1) * np.true_divide(float(q), np.float32(100))         # float32, like numpy/lib/_function_base_impl.py
+        lo = min(max(int(np.floor(virt)), 0), n - 1)
         hi = min(lo + 1, n - 1)
-        plan.append((len(ranks), pos - lo))
+        plan.append((len(ranks), np.float32(virt - np.float32(lo))))
         ranks += [lo, hi]
     vals: List[np.float32] = []
     for i in range(0, len(ranks), 4):
         vals += order_statistics(eng, x, ranks[i:i + 4])
     out = []
-    for first, frac in plan:
-        pair = np.array([vals[first], vals[first + 1]], np.float32)
-        out.append(float(np.percentile(pair, frac * 100.0)))               # NumPy's own interpolation formula and dtype
+    for first, t in plan:
+        a, b = vals[first], vals[first + 1]
+        d = np.subtract(b, a)
+        r = np.subtract(b, d * (1 - t)) if t >= 0.5 else np.add(a, d * t)
+        out.append(float(r))
     return out
 
 

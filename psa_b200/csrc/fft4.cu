@@ -90,9 +90,10 @@ struct StoreOut {
   }
 };
 
-template <int N1>
-__global__ void __launch_bounds__(kThreads, 2) fft4_kernel(Args a) {
-  using G = Geo<N1>;
+template <int N1, int T>
+__global__ void __launch_bounds__(T, 512 / T) fft4_kernel(Args a) {
+  using G = Geo<N1, T>;
+  constexpr int kThreads = T, kN1Tile = G::w;
   extern __shared__ double2 f4_smem[];
   c2* exch = reinterpret_cast<c2*>(f4_smem);
   c2* twb = exch + G::exchange_elems;                     // w_N1^(j s), rows of 17
@@ -125,13 +126,15 @@ __global__ void __launch_bounds__(kThreads, 2) fft4_kernel(Args a) {
         LoadP load{a.P + ((int64_t)(2 * k) * 3 + pol) * a.ldp, a.P + ((int64_t)(2 * k + 1) * 3 + pol) * a.ldp, a.window};
         // the loads do not depend on the ring slot: issue them before joining the wait
         c2* y_col = reinterpret_cast<c2*>(a.ybuf) + ((int64_t)(g % a.ring) * kColsPerGroup + c_local) * G::n;
-        stage_a_pass1<N1>(tid, n1_0, load, w128, exch);
+        stage_a_pass1<N1, T>(tid, n1_0, load, w128, exch);
         __syncthreads();                                   // exchange complete; tid 0 has seen the slot free
-        stage_a_pass2<N1>(tid, n1_0, exch, tw, y_col);
-        __threadfence();                                   // Y visible GPU-wide before the count goes up
+        stage_a_pass2<N1, T>(tid, n1_0, exch, tw, y_col);
       }
-      __syncthreads();
-      if (tid == 0) atomicAdd(a.done_a + g, 1);
+      __syncthreads();                                     // every thread's Y stores precede the barrier ...
+      if (tid == 0) {
+        __threadfence();                                   // ... and become visible GPU-wide before the count goes up
+        atomicAdd(a.done_a + g, 1);
+      }
     } else {                                               // ---------------- stage B tile
       const int g = phase - a.lag;
       if (g < 0 || g >= a.n_groups) continue;
@@ -139,12 +142,12 @@ __global__ void __launch_bounds__(kThreads, 2) fft4_kernel(Args a) {
       if (tid == 0) wait_count(a.done_a + g, TPG);         // all 16 columns of the group are in Y
       __syncthreads();
       LoadY<N1> load_y{a.ybuf + (int64_t)(g % a.ring) * kColsPerGroup * G::n, k2_0};
-      stage_b_pass1<N1>(tid, load_y, twb, exch);
+      stage_b_pass1<N1, T>(tid, load_y, twb, exch);
       __syncthreads();                                     // Y of this tile is in registers / shared memory
       if (tid == 0) atomicAdd(a.done_b + g, 1);
       StoreOut<N1> sink{a.out + (int64_t)g * kColsPerGroup, a.fstride, k2_0, min(kColsPerGroup, a.n_cols - g * kColsPerGroup),
                         a.inv_n};
-      stage_b_pass2<N1>(tid, exch, sink);
+      stage_b_pass2<N1, T>(tid, exch, sink);
     }
   }
 }
@@ -156,19 +159,28 @@ static int n1_of(int64_t n_t) {
   return 0;
 }
 
-template <int N1>
-static size_t smem_bytes() { return (size_t)(Geo<N1>::exchange_elems + Geo<N1>::q * 17) * sizeof(double2); }
+template <int N1, int T>
+static size_t smem_bytes() { return (size_t)(Geo<N1, T>::exchange_elems + Geo<N1, T>::q * 17) * sizeof(double2); }
+
+// threads per CTA: 128 (four CTAs per SM) where a 2048-point stage-B tile still spans 16 columns, else 256
+static int threads_of(int n1) {
+  static const int forced = getenv("PSA_FFT4_THREADS") ? atoi(getenv("PSA_FFT4_THREADS")) : 0;
+  if (n1 == 256) return 256;
+  return forced == 256 ? 256 : 128;
+}
 
 struct Schedule {
-  int n_groups, lag, ring, resident;
+  int n_groups, lag, ring, resident, tpg;
   int64_t ctl_bytes, y_bytes;
 };
 
 static Schedule make_schedule(int64_t n_t, int64_t n_cols, int sms) {
   Schedule s;
-  const int n1 = n1_of(n_t), tpg = n1 / 2;
+  const int n1 = n1_of(n_t), threads = threads_of(n1);
+  const int tpg = kColsPerGroup * n1 / (threads / 8);       // Geo<N1, T>::tiles_per_group
+  s.tpg = tpg;
   s.n_groups = (int)((n_cols + kColsPerGroup - 1) / kColsPerGroup);
-  s.resident = 2 * sms;
+  s.resident = (512 / threads) * sms;
   // Tile numbering: phase p = [A-tiles of group p | B-tiles of group p - lag].  Between the last A-tile of a group
   // and its first B-tile lie lag * 2 tpg tiles; between the last B-tile of a group and the first A-tile that reuses
   // its ring slot, (ring - lag - 1) * 2 tpg.  Both distances exceed the number of resident CTAs, so that a tile
@@ -205,14 +217,15 @@ int64_t fft4_workspace_bytes(int64_t n_t, int64_t n_k) {
   return s.ctl_bytes + s.y_bytes;
 }
 
-template <int N1>
+template <int N1, int T>
 static int launch_one(const fft4::Args& a, const fft4::Schedule& sch, cudaStream_t s) {
   using namespace fft4;
-  const size_t smem = smem_bytes<N1>();
-  PSA_CUDA(cudaFuncSetAttribute(fft4_kernel<N1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t tiles = (int64_t)sch.n_groups * 2 * Geo<N1>::tiles_per_group;
+  static_assert(Geo<N1, T>::tiles_per_group > 0, "geometry");
+  const size_t smem = smem_bytes<N1, T>();
+  PSA_CUDA(cudaFuncSetAttribute(fft4_kernel<N1, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t tiles = (int64_t)sch.n_groups * 2 * Geo<N1, T>::tiles_per_group;
   const int grid = (int)(tiles < sch.resident ? tiles : sch.resident);
-  fft4_kernel<N1><<<grid, kThreads, smem, s>>>(a);
+  fft4_kernel<N1, T><<<grid, T, smem, s>>>(a);
   return launch_status("fft4_kernel");
 }
 
@@ -259,12 +272,12 @@ int launch_fft4(const float* P, int64_t n_k, int64_t n_t, int64_t ldp, const voi
   a.n_groups = sch.n_groups;
   a.lag = sch.lag;
   a.ring = sch.ring;
-  const int n1 = n1_of(n_t);
-  a.total_items = (sch.n_groups + sch.lag) * 2 * (n1 / 2);
+  const int n1 = n1_of(n_t), threads = threads_of(n1);
+  a.total_items = (sch.n_groups + sch.lag) * 2 * sch.tpg;
   a.inv_n = 1.0 / (double)n_t;
-  if (n1 == 64) return launch_one<64>(a, sch, s);
-  if (n1 == 128) return launch_one<128>(a, sch, s);
-  return launch_one<256>(a, sch, s);
+  if (n1 == 64) return threads == 128 ? launch_one<64, 128>(a, sch, s) : launch_one<64, 256>(a, sch, s);
+  if (n1 == 128) return threads == 128 ? launch_one<128, 128>(a, sch, s) : launch_one<128, 256>(a, sch, s);
+  return launch_one<256, 256>(a, sch, s);
 }
 
 }  // namespace psa

@@ -33,10 +33,10 @@ F4_HD c2 cmul(c2 a, c2 b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b
 F4_HD c2 mul_neg_i(c2 a) { return mk(a.y, -a.x); }
 
 constexpr int kN2 = 128;            // stage A transform length (over n2)
-constexpr int kTilePoints = 4096;   // points per tile of either stage
-constexpr int kThreads = 256;       // 16 points per thread in every pass
 constexpr int kColsPerGroup = 16;   // adjacent (k, pol) columns stored together (128 bytes per frequency)
-constexpr int kN1Tile = 32;         // n1 values per stage-A tile (one 128-byte run of float32 per n2)
+// A tile of either stage is 16 points per thread: T = 256 threads -> 4096 points (64 KiB exchange, 2 CTAs per SM),
+// T = 128 -> 2048 points (32 KiB, 4 CTAs per SM: the same warps per SM, but four independent tile phases instead of
+// two, and barriers that only span four warps).
 
 // forward DFTs in registers, natural output order
 F4_HD void bfly4(c2& a0, c2& a1, c2& a2, c2& a3) {
@@ -91,27 +91,32 @@ F4_HD void dftq(c2 (&x)[Q]) {
 }
 
 // ------------------------------------------------------------------------------------------------ geometry
-template <int N1>
+template <int N1, int T>
 struct Geo {
   static constexpr int n = N1 * kN2;
+  static constexpr int tile_points = 16 * T;
+  static constexpr int w = T / 8;                            // n1 values per stage-A tile (a 64- or 128-byte run per n2)
   static constexpr int q = N1 / 16;                          // second-pass length of stage B (4, 8, 16)
-  static constexpr int k2_per_tile = kTilePoints / (kColsPerGroup * N1);   // 4, 2, 1
-  static constexpr int transforms = kColsPerGroup * k2_per_tile;          // stage-B transforms per tile (64, 32, 16)
+  static constexpr int k2_per_tile = tile_points / (kColsPerGroup * N1);
+  static constexpr int transforms = kColsPerGroup * k2_per_tile;          // stage-B transforms per tile
   static constexpr int S = N1 + 1;                           // exchange stride of one transform (odd: conflict-free reads)
-  static constexpr int tiles_per_group = N1 / 2;             // of either stage, per 16-column group
-  static constexpr int a_tiles_per_column = N1 / kN1Tile;
-  static constexpr int exchange_elems = (transforms * S > kTilePoints) ? transforms * S : kTilePoints;
+  static constexpr int a_tiles_per_column = N1 / w;
+  static constexpr int tiles_per_group = kColsPerGroup * a_tiles_per_column;   // of either stage, per 16-column group
+  static constexpr int exchange_elems = (transforms * S > tile_points) ? transforms * S : tile_points;
+  static_assert(k2_per_tile >= 1 && kN2 % k2_per_tile == 0 && kN2 / k2_per_tile == tiles_per_group, "tile geometry");
+  static_assert(transforms * q == T, "stage B: one thread per (transform, j)");
 };
 
 // ------------------------------------------------------------------------------------------------ stage A
-// Tile: one column, n1 in [n1_0, n1_0 + 32).  Thread: lane = n1 - n1_0, warp = j (0..7).
-// pass 1: x[n1 + N1 (j + 8 i)], i < 16  -> radix 16 over i -> y_s[j] * w_128^(j s)  -> exchange[s][j][lane]
-// pass 2: exchange[s][0..8)[lane] for s = warp, warp + 8 -> radix 8 over j -> k2 = 16 m + s
+// Tile: one column, n1 in [n1_0, n1_0 + w), w = T / 8.  Thread: l = n1 - n1_0 = tid % w, j = tid / w (0..7).
+// pass 1: x[n1 + N1 (j + 8 i)], i < 16  -> radix 16 over i -> y_s[j] * w_128^(j s)  -> exchange[s][j][l]
+// pass 2: exchange[s][0..8)[l] for s = j, j + 8 -> radix 8 over j -> k2 = 16 m + s
 //         -> * w_n^(n1 k2) -> Y[k2][n1]
 // w128: the 128 values w_128^e (constant memory on the device); tw: w_n^e, e < n.
-template <int N1, class LoadF>
+template <int N1, int T, class LoadF>
 F4_HD void stage_a_pass1(int tid, int n1_0, const LoadF& load, const c2* w128, c2* exch) {
-  const int lane = tid & 31, j = tid >> 5;
+  constexpr int W = Geo<N1, T>::w;
+  const int lane = tid % W, j = tid / W;
   c2 x[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) x[i] = load(n1_0 + lane + N1 * (j + 8 * i));
@@ -120,13 +125,14 @@ F4_HD void stage_a_pass1(int tid, int n1_0, const LoadF& load, const c2* w128, c
   for (int s = 0; s < 16; ++s) {
     c2 v = x[out16(s)];
     if (s != 0) v = cmul(v, w128[j * s]);
-    exch[(s * 8 + j) * 32 + lane] = v;
+    exch[(s * 8 + j) * W + lane] = v;
   }
 }
 
-template <int N1>
+template <int N1, int T>
 F4_HD void stage_a_pass2(int tid, int n1_0, const c2* exch, const c2* tw, c2* y_col) {
-  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int W = Geo<N1, T>::w;
+  const int lane = tid % W, warp = tid / W;
   const int n1 = n1_0 + lane;
   const c2 step = tw[16 * n1];                               // w_n^(16 n1): from k2 to k2 + 16
 #pragma unroll
@@ -134,7 +140,7 @@ F4_HD void stage_a_pass2(int tid, int n1_0, const c2* exch, const c2* tw, c2* y_
     const int s = warp + 8 * half;
     c2 x[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = exch[(s * 8 + j) * 32 + lane];
+    for (int j = 0; j < 8; ++j) x[j] = exch[(s * 8 + j) * W + lane];
     dft8(x);
     c2 w = tw[n1 * s];                                       // w_n^(n1 s)
 #pragma unroll
@@ -152,9 +158,9 @@ F4_HD void stage_a_pass2(int tid, int n1_0, const c2* exch, const c2* tw, c2* y_
 //         quarter-warp pairs transforms tau and tau + 4 so that its 8 shared-memory stores hit 8 distinct bank groups.
 // pass 2: thread (c = tid & 15, k2l, u): exch[tau S + (u + q v) q + j], j < q -> radix q -> k1 = 16 m + u + q v.
 //         lanes run over the 16 columns: every store instruction writes 128 contiguous bytes per half-warp.
-template <int N1>
+template <int N1, int T>
 F4_HD void stage_b_thread_pass1(int tid, int& tau, int& j) {
-  constexpr int q = Geo<N1>::q;
+  constexpr int q = Geo<N1, T>::q;
   if constexpr (q == 4) {                                    // warp = 8 transforms: lane = j + 4 h + 8 k', tau = 8 warp + k' + 4 h
     const int lane = tid & 31, warp = tid >> 5;
     j = lane & 3;
@@ -165,11 +171,11 @@ F4_HD void stage_b_thread_pass1(int tid, int& tau, int& j) {
   }
 }
 
-template <int N1, class LoadY>
+template <int N1, int T, class LoadY>
 F4_HD void stage_b_pass1(int tid, const LoadY& load_y, const c2* twb, c2* exch) {
-  constexpr int q = Geo<N1>::q, S = Geo<N1>::S;
+  constexpr int q = Geo<N1, T>::q, S = Geo<N1, T>::S;
   int tau, j;
-  stage_b_thread_pass1<N1>(tid, tau, j);
+  stage_b_thread_pass1<N1, T>(tid, tau, j);
   c2 x[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) x[i] = load_y(tau, j + q * i);
@@ -183,9 +189,9 @@ F4_HD void stage_b_pass1(int tid, const LoadY& load_y, const c2* twb, c2* exch) 
 }
 
 // sink(c, k2l, k1, value): called for the 16 outputs of this thread
-template <int N1, class Sink>
+template <int N1, int T, class Sink>
 F4_HD void stage_b_pass2(int tid, const c2* exch, Sink& sink) {
-  constexpr int q = Geo<N1>::q, S = Geo<N1>::S;
+  constexpr int q = Geo<N1, T>::q, S = Geo<N1, T>::S;
   const int c = tid & 15, g = tid >> 4;
   const int k2l = g / q, u = g % q;
   const int tau = k2l * 16 + c;

@@ -32,9 +32,10 @@ static void fft_ref(std::vector<cplx>& a) {                 // iterative radix-2
   }
 }
 
-template <int N1>
+template <int N1, int T>
 static double run() {
-  typedef Geo<N1> G;
+  typedef Geo<N1, T> G;
+  const int kThreads = T, kN1Tile = G::w;
   const int n = G::n, cols = kColsPerGroup;
   std::vector<c2> w128(128), tw(n), twb(G::q * 17);
   for (int e = 0; e < 128; ++e) w128[e] = mk(std::cos(-2 * M_PI * e / 128.0), std::sin(-2 * M_PI * e / 128.0));
@@ -53,8 +54,8 @@ static double run() {
     for (int tile = 0; tile < G::a_tiles_per_column; ++tile) {
       const int n1_0 = tile * kN1Tile;
       auto load = [&](int t) { return mk(x[c][t].real(), x[c][t].imag()); };
-      for (int tid = 0; tid < kThreads; ++tid) stage_a_pass1<N1>(tid, n1_0, load, w128.data(), exch.data());
-      for (int tid = 0; tid < kThreads; ++tid) stage_a_pass2<N1>(tid, n1_0, exch.data(), tw.data(), y.data() + (size_t)c * n);
+      for (int tid = 0; tid < kThreads; ++tid) stage_a_pass1<N1, T>(tid, n1_0, load, w128.data(), exch.data());
+      for (int tid = 0; tid < kThreads; ++tid) stage_a_pass2<N1, T>(tid, n1_0, exch.data(), tw.data(), y.data() + (size_t)c * n);
     }
   // stage B: every k2 tile of the group
   std::vector<std::vector<cplx>> got(cols, std::vector<cplx>(n));
@@ -62,13 +63,13 @@ static double run() {
   for (int tile = 0; tile < G::tiles_per_group; ++tile) {
     const int k2_0 = tile * G::k2_per_tile;
     auto load_y = [&](int tau, int n1) { return y[((size_t)(tau & 15) * kN2 + k2_0 + (tau >> 4)) * N1 + n1]; };
-    for (int tid = 0; tid < kThreads; ++tid) stage_b_pass1<N1>(tid, load_y, twb.data(), exch.data());
+    for (int tid = 0; tid < kThreads; ++tid) stage_b_pass1<N1, T>(tid, load_y, twb.data(), exch.data());
     auto sink = [&](int c, int k2l, int k1, c2 v) {
       const int f = k2_0 + k2l + kN2 * k1;
       got[c][f] = cplx(v.x, v.y);
       ++hits[(size_t)c * n + f];
     };
-    for (int tid = 0; tid < kThreads; ++tid) stage_b_pass2<N1>(tid, exch.data(), sink);
+    for (int tid = 0; tid < kThreads; ++tid) stage_b_pass2<N1, T>(tid, exch.data(), sink);
   }
   double worst = 0.0;
   for (int c = 0; c < cols; ++c) {
@@ -85,7 +86,9 @@ static double run() {
 }
 
 int main() {
-  const double e64 = run<64>(), e128 = run<128>(), e256 = run<256>();
-  std::printf("OK %.3e %.3e %.3e\n", e64, e128, e256);
-  return (e64 < 1e-13 && e128 < 1e-13 && e256 < 1e-13) ? 0 : 1;
+  const double e[5] = {run<64, 256>(), run<128, 256>(), run<256, 256>(), run<64, 128>(), run<128, 128>()};
+  std::printf("OK %.3e %.3e %.3e %.3e %.3e\n", e[0], e[1], e[2], e[3], e[4]);
+  for (double v : e)
+    if (!(v < 1e-13)) return 1;
+  return 0;
 }
