@@ -115,27 +115,41 @@ struct IsedAtom {
   int m_begin, m_end;
 };
 
-__device__ __forceinline__ void ised_values(const IsedBatch& b, const IsedAtom& at, int p, double2 cs, float dv, float ml,
-                                            float (&val)[3], float& running_max) {
-  float w[3] = {0.f, 0.f, 0.f};
-  if (at.m_end - at.m_begin == 1) {                        // the usual case: disjoint groups
+// w / d in float32, correctly rounded (== __fdiv_rn, the reference's `wiggles /= max`), for a divisor that is the same
+// for a whole launch: r = RN(1 / d) is formed once, then q = w r is corrected twice with exact FMA residuals
+// (Markstein).  5 FMA-pipe instructions instead of the ~15 of a general IEEE division; operands outside a safe
+// exponent window (denormal quotients, overflow) take the general path.
+struct FastDiv {
+  float d, r;
+  bool usable;
+  __device__ __forceinline__ explicit FastDiv(float div) : d(div), r(__frcp_rn(div)) {
+    const float ad = fabsf(div);
+    usable = ad > 1e-12f && ad < 1e12f;
+  }
+  __device__ __forceinline__ float operator()(float w) const {
+    const float aw = fabsf(w);
+    if (usable && aw > 1e-24f && aw < 1e24f) {
+      float q = __fmul_rn(w, r);
+      q = __fmaf_rn(__fmaf_rn(-q, d, w), r, q);
+      q = __fmaf_rn(__fmaf_rn(-q, d, w), r, q);
+      return q;
+    }
+    return __fdiv_rn(w, d);
+  }
+};
+
+__device__ __forceinline__ void ised_values(const IsedBatch& b, const IsedAtom& at, int p, double2 cs, float (&w)[3],
+                                            float& running_max) {
+  w[0] = w[1] = w[2] = 0.f;
+  for (int m = at.m_begin; m < at.m_end; ++m) {            // float32 running sum, group by group
+    double U[3], V[3];
+    ised_uv(b, p, __ldg(b.member_grp + m), at.ca, at.sa, U, V);
 #pragma unroll
-    for (int pol = 0; pol < 3; ++pol) w[pol] = (float)(cs.x * at.U[pol] + cs.y * at.V[pol]);
-#pragma unroll
-    for (int pol = 0; pol < 3; ++pol) running_max = fmaxf(running_max, fabsf(w[pol]));
-  } else {                                                 // overlapping groups: float32 running sum, group by group
-    for (int m = at.m_begin; m < at.m_end; ++m) {
-      double U[3], V[3];
-      ised_uv(b, p, __ldg(b.member_grp + m), at.ca, at.sa, U, V);
-#pragma unroll
-      for (int pol = 0; pol < 3; ++pol) {
-        w[pol] = (float)((double)w[pol] + (cs.x * U[pol] + cs.y * V[pol]));
-        running_max = fmaxf(running_max, fabsf(w[pol]));   // the reference's running maximum (after every group)
-      }
+    for (int pol = 0; pol < 3; ++pol) {
+      w[pol] = (float)((double)w[pol] + (cs.x * U[pol] + cs.y * V[pol]));
+      running_max = fmaxf(running_max, fabsf(w[pol]));     // the reference's running maximum (after every group)
     }
   }
-#pragma unroll
-  for (int pol = 0; pol < 3; ++pol) val[pol] = __fadd_rn(at.mean[pol], __fmul_rn(__fdiv_rn(w[pol], dv), ml));
 }
 
 // kWrite = false: max over (frame, atom of a group, pol) of |running sum after that group| per point -> wmax[p]
@@ -170,12 +184,32 @@ __global__ void __launch_bounds__(128) ised_batch_kernel(IsedBatch b, const floa
     if (at.m_end - at.m_begin == 1) ised_uv(b, p, __ldg(b.member_grp + at.m_begin), at.ca, at.sa, at.U, at.V);
   }
   const float dv = kWrite ? __ldg(div + p) : 1.f, ml = kWrite ? __ldg(mul + p) : 1.f;
+  const bool rescale = dv != 1.f || ml != 1.f;                               // uniform over the block
+  const FastDiv fdiv(dv);
+  const bool single = at.m_end - at.m_begin == 1;                            // the usual case: disjoint groups
   float* o = kWrite ? out + (int64_t)p * b.n_frames * b.n_a * 3 : nullptr;
   const int n_warp = (int)min((int64_t)32, b.n_a - a_warp);                 // atoms of this warp that exist (<= 0: none)
   for (int f = 0; f < b.n_frames; ++f) {
-    float val[3] = {0.f, 0.f, 0.f};
-    if (live) ised_values(b, at, p, phasor[f], dv, ml, val, local_max);
+    const double2 cs = phasor[f];
+    float w[3] = {0.f, 0.f, 0.f};
+    if (live) {
+      if (single) {
+#pragma unroll
+        for (int pol = 0; pol < 3; ++pol) {
+          w[pol] = (float)(cs.x * at.U[pol] + cs.y * at.V[pol]);
+          if (!kWrite) local_max = fmaxf(local_max, fabsf(w[pol]));
+        }
+      } else {
+        ised_values(b, at, p, cs, w, local_max);
+      }
+    }
     if (!kWrite) continue;
+    float val[3];
+#pragma unroll
+    for (int pol = 0; pol < 3; ++pol) {
+      const float scaled = rescale ? __fmul_rn(fdiv(w[pol]), ml) : w[pol];
+      val[pol] = __fadd_rn(at.mean[pol], scaled);
+    }
     float* row = o + ((int64_t)f * b.n_a + a_warp) * 3;
     if (kWide) {
       float* st = stage[warp][f & 1];
@@ -184,7 +218,7 @@ __global__ void __launch_bounds__(128) ised_batch_kernel(IsedBatch b, const floa
       st[lane * 3 + 2] = val[2];
       __syncwarp();
       if (lane * 4 < n_warp * 3)                                            // n_warp % 4 == 0 here: whole float4s only
-        reinterpret_cast<float4*>(row)[lane] = reinterpret_cast<const float4*>(st)[lane];
+        __stcs(reinterpret_cast<float4*>(row) + lane, reinterpret_cast<const float4*>(st)[lane]);
       // the other buffer is written next; this one again two frames from now, after the next __syncwarp
     } else if (live) {
       row[lane * 3] = val[0];

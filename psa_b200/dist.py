@@ -74,11 +74,18 @@ class SharedHostArray:
         nbytes = max(1, int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize)
         distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         rank = dist.get_rank(group) if distributed else src
+        self._shm, self.array, self.ptr, self.nbytes, self._registered = None, None, 0, nbytes, False
         if rank == src:
-            self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            try:
+                self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            except OSError as exc:                       # /dev/shm too small (containers often cap it at 64 MB)
+                self.error = f"cannot create {nbytes} bytes of POSIX shared memory: {exc}"
         if distributed:
-            box = [self._shm.name if rank == src else None]
+            box = [self._shm.name if self._shm is not None else None]
             dist.broadcast_object_list(box, src=src, group=group)
+            if box[0] is None:
+                self.error = getattr(self, "error", "the source rank could not create the shared segment")
+                return
             if rank != src:
                 self._shm = shared_memory.SharedMemory(name=box[0])
                 try:        # the creator owns the name; keep Python's tracker from unlinking it a second time at exit
@@ -86,18 +93,22 @@ class SharedHostArray:
                 except Exception:
                     pass
             dist.barrier(group=group)                    # everybody has mapped the segment
+        if self._shm is None:
+            return
         if rank == src:
             self._shm.unlink()
         self.array = np.ndarray(self.shape, self.dtype, buffer=self._shm.buf)
         self.ptr = ctypes.addressof(ctypes.c_char.from_buffer(self._shm.buf))
-        self.nbytes = nbytes
-        self._registered = False
         if register is None:
             register = torch.cuda.is_available()
         if register:
             from . import _lib
             _lib.call("psa_host_register", self.ptr, nbytes)
             self._registered = True
+
+    @property
+    def available(self) -> bool:
+        return self.array is not None
 
     def close(self) -> None:
         if getattr(self, "_shm", None) is None:
@@ -433,6 +444,15 @@ def calculate_sharded(calc, k_points_mags: np.ndarray, k_vectors_3d: np.ndarray,
 
         # 2. every rank: its contiguous k-slice, no communication; spectra stream out over this rank's own PCIe link
         k0, k1 = shard_range(n_k, rank, world)
+        if not shared.available:
+            # no shared segment on this box: the slices are gathered on the source GPU and leave through its link
+            local = sed_on_device(dtraj, k_vecs[k0:k1], proj_groups, complex_out, calc.use_displacements,
+                                  k_chunk=k_chunk_size)
+            full = gather_k_slices(local, n_k, dst=src, group=group)
+            if rank != src:
+                return None
+            return SED(calc._to_host(full), np.fft.fftfreq(n_t, d=calc.dt_ps), k_points_mags, k_vectors_3d,
+                       k_grid_shape=k_grid_shape, is_complex=complex_out, phase=None, context=calc._context(groups))
         if k1 > k0 and n_t > 0:
             sed_on_device(dtraj, k_vecs[k0:k1], proj_groups, complex_out, calc.use_displacements, k_chunk=k_chunk_size,
                           host_out=HostTarget(shared.ptr, n_k, k0, n_t, shared))

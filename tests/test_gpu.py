@@ -545,7 +545,7 @@ def test_device_side_consumers_match_numpy(eng, gold_si):
     np.testing.assert_allclose(res.sed, want, rtol=3e-7)
     st = res.context["stats"]
     np.testing.assert_allclose([st["global_min"], st["global_max"]], [res.sed.min(), res.sed.max()], rtol=0)
-    assert [st["vmin"], st["vmax"]] == [float(v) for v in np.percentile(res.sed, [1.0, 99.0])]
+    assert [st["vmin"], st["vmax"]] == [float(np.percentile(res.sed, q)) for q in (1.0, 99.0)]   # scalar q, like the plotter
 
 
 def test_cli_batch_driver(gold_si, tmp_path):
