@@ -90,14 +90,17 @@ struct StoreOut {
   }
 };
 
-template <int N1, int T>
-__global__ void __launch_bounds__(T, 512 / T) fft4_kernel(Args a) {
+// OCC = CTAs per SM the register allocation is capped for: the butterflies hold 16 complex128 values (64 registers)
+// and ptxas fits the whole tile loop in 80 registers with a few bytes of spill, so six 128-thread CTAs (24 warps,
+// six independent tile phases) share an SM.
+template <int N1, int T, int OCC>
+__global__ void __launch_bounds__(T, OCC) fft4_kernel(Args a) {
   using G = Geo<N1, T>;
   constexpr int kThreads = T, kN1Tile = G::w;
   extern __shared__ double2 f4_smem[];
   c2* exch = reinterpret_cast<c2*>(f4_smem);
   c2* twb = exch + G::exchange_elems;                     // w_N1^(j s), rows of 17
-  __shared__ int s_item;
+  __shared__ int s_item[2];
   const int tid = threadIdx.x;
   for (int i = tid; i < G::q * 17; i += kThreads) {
     const int j = i / 17, s = i % 17;
@@ -108,46 +111,66 @@ __global__ void __launch_bounds__(T, 512 / T) fft4_kernel(Args a) {
   const c2* tw = reinterpret_cast<const c2*>(a.tw);
   constexpr int TPG = G::tiles_per_group;
 
-  for (;;) {
-    __syncthreads();                                       // previous tile's shared-memory reads are finished
-    if (tid == 0) s_item = atomicAdd(a.counter, 1);
-    __syncthreads();
-    const int item = s_item;
-    if (item >= a.total_items) break;
+  // Tiles come from an atomic counter; the NEXT tile is taken while the current one is being processed, so the
+  // counter's round trip and the first touch of the next stage-A tile's input (an L2 prefetch) hide under the
+  // butterflies.  (Still deadlock-free: every CTA takes tiles in increasing order and works them off in order, so
+  // the smallest unfinished tile is always some CTA's current tile, and it only waits for smaller ones.)
+  if (tid == 0) s_item[0] = atomicAdd(a.counter, 1);
+  __syncthreads();
+  int item = s_item[0];
+  for (int it = 0; item < a.total_items; ++it) {
+    if (tid == 0) s_item[(it + 1) & 1] = atomicAdd(a.counter, 1);
     const int phase = item / (2 * TPG), r = item % (2 * TPG);
     if (r < TPG) {                                         // ---------------- stage A tile
       const int g = phase;
-      if (g >= a.n_groups) continue;
-      const int c_local = r / G::a_tiles_per_column, n1_0 = (r % G::a_tiles_per_column) * kN1Tile;
-      const int col = g * kColsPerGroup + c_local;
-      if (g >= a.ring && tid == 0) wait_count(a.done_b + g - a.ring, TPG);     // the slot's previous group has been read
-      if (col < a.n_cols) {
-        const int k = col / 3, pol = col % 3;
-        LoadP load{a.P + ((int64_t)(2 * k) * 3 + pol) * a.ldp, a.P + ((int64_t)(2 * k + 1) * 3 + pol) * a.ldp, a.window};
-        // the loads do not depend on the ring slot: issue them before joining the wait
-        c2* y_col = reinterpret_cast<c2*>(a.ybuf) + ((int64_t)(g % a.ring) * kColsPerGroup + c_local) * G::n;
-        stage_a_pass1<N1, T>(tid, n1_0, load, w128, exch);
-        __syncthreads();                                   // exchange complete; tid 0 has seen the slot free
-        stage_a_pass2<N1, T>(tid, n1_0, exch, tw, y_col);
-      }
-      __syncthreads();                                     // every thread's Y stores precede the barrier ...
-      if (tid == 0) {
-        __threadfence();                                   // ... and become visible GPU-wide before the count goes up
-        atomicAdd(a.done_a + g, 1);
+      if (g < a.n_groups) {
+        const int c_local = r / G::a_tiles_per_column, n1_0 = (r % G::a_tiles_per_column) * kN1Tile;
+        const int col = g * kColsPerGroup + c_local;
+        if (g >= a.ring && tid == 0) wait_count(a.done_b + g - a.ring, TPG);   // the slot's previous group has been read
+        if (col < a.n_cols) {
+          const int k = col / 3, pol = col % 3;
+          LoadP load{a.P + ((int64_t)(2 * k) * 3 + pol) * a.ldp, a.P + ((int64_t)(2 * k + 1) * 3 + pol) * a.ldp, a.window};
+          c2* y_col = reinterpret_cast<c2*>(a.ybuf) + ((int64_t)(g % a.ring) * kColsPerGroup + c_local) * G::n;
+          stage_a_pass1<N1, T>(tid, n1_0, load, w128, exch);       // loads first: they do not depend on the ring slot
+          __syncthreads();                                 // exchange complete; tid 0 has seen the slot free
+          stage_a_pass2<N1, T>(tid, n1_0, exch, tw, y_col);
+        }
+        __syncthreads();                                   // every thread's Y stores precede the barrier ...
+        if (tid == 0) {
+          __threadfence();                                 // ... and become visible GPU-wide before the count goes up
+          atomicAdd(a.done_a + g, 1);
+        }
       }
     } else {                                               // ---------------- stage B tile
       const int g = phase - a.lag;
-      if (g < 0 || g >= a.n_groups) continue;
-      const int k2_0 = (r - TPG) * G::k2_per_tile;
-      if (tid == 0) wait_count(a.done_a + g, TPG);         // all 16 columns of the group are in Y
-      __syncthreads();
-      LoadY<N1> load_y{a.ybuf + (int64_t)(g % a.ring) * kColsPerGroup * G::n, k2_0};
-      stage_b_pass1<N1, T>(tid, load_y, twb, exch);
-      __syncthreads();                                     // Y of this tile is in registers / shared memory
-      if (tid == 0) atomicAdd(a.done_b + g, 1);
-      StoreOut<N1> sink{a.out + (int64_t)g * kColsPerGroup, a.fstride, k2_0, min(kColsPerGroup, a.n_cols - g * kColsPerGroup),
-                        a.inv_n};
-      stage_b_pass2<N1, T>(tid, exch, sink);
+      if (g >= 0 && g < a.n_groups) {
+        const int k2_0 = (r - TPG) * G::k2_per_tile;
+        if (tid == 0) wait_count(a.done_a + g, TPG);       // all 16 columns of the group are in Y
+        __syncthreads();
+        LoadY<N1> load_y{a.ybuf + (int64_t)(g % a.ring) * kColsPerGroup * G::n, k2_0};
+        stage_b_pass1<N1, T>(tid, load_y, twb, exch);
+        __syncthreads();                                   // Y of this tile is in registers / shared memory
+        if (tid == 0) atomicAdd(a.done_b + g, 1);
+        StoreOut<N1> sink{a.out + (int64_t)g * kColsPerGroup, a.fstride, k2_0, min(kColsPerGroup, a.n_cols - g * kColsPerGroup),
+                          a.inv_n};
+        stage_b_pass2<N1, T>(tid, exch, sink);
+      }
+    }
+    __syncthreads();                                       // this tile's shared-memory reads are finished; s_item is set
+    item = s_item[(it + 1) & 1];
+    // first touch of the next stage-A tile's samples: pull its lines into L2 while nothing depends on them yet
+    if (item < a.total_items && item % (2 * TPG) < TPG) {
+      const int rn = item % (2 * TPG), gn = item / (2 * TPG);
+      const int col = gn * kColsPerGroup + rn / G::a_tiles_per_column;
+      if (gn < a.n_groups && col < a.n_cols) {
+        const int k = col / 3, pol = col % 3, n1_0 = (rn % G::a_tiles_per_column) * kN1Tile;
+        const float* re = a.P + ((int64_t)(2 * k) * 3 + pol) * a.ldp + n1_0;
+        const float* im = a.P + ((int64_t)(2 * k + 1) * 3 + pol) * a.ldp + n1_0;
+        for (int n2 = tid; n2 < 2 * kN2; n2 += T) {
+          const float* ptr = (n2 < kN2 ? re : im) + (int64_t)(n2 & (kN2 - 1)) * N1;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+        }
+      }
     }
   }
 }
@@ -162,11 +185,17 @@ static int n1_of(int64_t n_t) {
 template <int N1, int T>
 static size_t smem_bytes() { return (size_t)(Geo<N1, T>::exchange_elems + Geo<N1, T>::q * 17) * sizeof(double2); }
 
-// threads per CTA: 128 (four CTAs per SM) where a 2048-point stage-B tile still spans 16 columns, else 256
+// threads per CTA: 128 where a 2048-point stage-B tile still spans 16 columns, else 256; CTAs per SM: 6 x 128 or
+// 3 x 256 threads (PSA_FFT4_THREADS / PSA_FFT4_OCC select the other compiled variants for A/B runs)
 static int threads_of(int n1) {
   static const int forced = getenv("PSA_FFT4_THREADS") ? atoi(getenv("PSA_FFT4_THREADS")) : 0;
   if (n1 == 256) return 256;
   return forced == 256 ? 256 : 128;
+}
+static int occ_of(int threads) {
+  static const int forced = getenv("PSA_FFT4_OCC") ? atoi(getenv("PSA_FFT4_OCC")) : 0;
+  if (threads == 128) return (forced == 4 || forced == 5) ? forced : 6;
+  return forced == 2 ? 2 : 3;
 }
 
 struct Schedule {
@@ -180,7 +209,7 @@ static Schedule make_schedule(int64_t n_t, int64_t n_cols, int sms) {
   const int tpg = kColsPerGroup * n1 / (threads / 8);       // Geo<N1, T>::tiles_per_group
   s.tpg = tpg;
   s.n_groups = (int)((n_cols + kColsPerGroup - 1) / kColsPerGroup);
-  s.resident = (512 / threads) * sms;
+  s.resident = occ_of(threads) * sms;
   // Tile numbering: phase p = [A-tiles of group p | B-tiles of group p - lag].  Between the last A-tile of a group
   // and its first B-tile lie lag * 2 tpg tiles; between the last B-tile of a group and the first A-tile that reuses
   // its ring slot, (ring - lag - 1) * 2 tpg.  Both distances exceed the number of resident CTAs, so that a tile
@@ -217,16 +246,28 @@ int64_t fft4_workspace_bytes(int64_t n_t, int64_t n_k) {
   return s.ctl_bytes + s.y_bytes;
 }
 
-template <int N1, int T>
-static int launch_one(const fft4::Args& a, const fft4::Schedule& sch, cudaStream_t s) {
+template <int N1, int T, int OCC>
+static int launch_occ(const fft4::Args& a, const fft4::Schedule& sch, cudaStream_t s) {
   using namespace fft4;
-  static_assert(Geo<N1, T>::tiles_per_group > 0, "geometry");
   const size_t smem = smem_bytes<N1, T>();
-  PSA_CUDA(cudaFuncSetAttribute(fft4_kernel<N1, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PSA_CUDA(cudaFuncSetAttribute(fft4_kernel<N1, T, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t tiles = (int64_t)sch.n_groups * 2 * Geo<N1, T>::tiles_per_group;
   const int grid = (int)(tiles < sch.resident ? tiles : sch.resident);
-  fft4_kernel<N1, T><<<grid, T, smem, s>>>(a);
+  fft4_kernel<N1, T, OCC><<<grid, T, smem, s>>>(a);
   return launch_status("fft4_kernel");
+}
+
+template <int N1, int T>
+static int launch_one(const fft4::Args& a, const fft4::Schedule& sch, cudaStream_t s) {
+  const int occ = fft4::occ_of(T);
+  if constexpr (T == 128) {
+    if (occ == 4) return launch_occ<N1, T, 4>(a, sch, s);
+    if (occ == 5) return launch_occ<N1, T, 5>(a, sch, s);
+    return launch_occ<N1, T, 6>(a, sch, s);
+  } else {
+    if (occ == 2) return launch_occ<N1, T, 2>(a, sch, s);
+    return launch_occ<N1, T, 3>(a, sch, s);
+  }
 }
 
 // coherent assembly only: complex64 out[f][k_offset + k][pol]

@@ -122,21 +122,25 @@ struct IsedAtom {
 struct FastDiv {
   float d, r;
   bool usable;
-  __device__ __forceinline__ explicit FastDiv(float div) : d(div), r(__frcp_rn(div)) {
-    const float ad = fabsf(div);
-    usable = ad > 1e-12f && ad < 1e12f;
-  }
-  __device__ __forceinline__ float operator()(float w) const {
-    const float aw = fabsf(w);
-    if (usable && aw > 1e-24f && aw < 1e24f) {
-      float q = __fmul_rn(w, r);
-      q = __fmaf_rn(__fmaf_rn(-q, d, w), r, q);
-      q = __fmaf_rn(__fmaf_rn(-q, d, w), r, q);
-      return q;
-    }
-    return __fdiv_rn(w, d);
-  }
 };
+__device__ __forceinline__ FastDiv make_fast_div(float div) {
+  FastDiv f;
+  f.d = div;
+  f.r = __frcp_rn(div);
+  const float ad = fabsf(div);
+  f.usable = ad > 1e-12f && ad < 1e12f;
+  return f;
+}
+__device__ __forceinline__ float fast_div(const FastDiv& f, float w) {
+  const float aw = fabsf(w);
+  if (f.usable && aw > 1e-24f && aw < 1e24f) {
+    float q = __fmul_rn(w, f.r);
+    q = __fmaf_rn(__fmaf_rn(-q, f.d, w), f.r, q);
+    q = __fmaf_rn(__fmaf_rn(-q, f.d, w), f.r, q);
+    return q;
+  }
+  return __fdiv_rn(w, f.d);
+}
 
 __device__ __forceinline__ void ised_values(const IsedBatch& b, const IsedAtom& at, int p, double2 cs, float (&w)[3],
                                             float& running_max) {
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(128) ised_batch_kernel(IsedBatch b, const floa
   }
   const float dv = kWrite ? __ldg(div + p) : 1.f, ml = kWrite ? __ldg(mul + p) : 1.f;
   const bool rescale = dv != 1.f || ml != 1.f;                               // uniform over the block
-  const FastDiv fdiv(dv);
+  const FastDiv fdiv = make_fast_div(dv);
   const bool single = at.m_end - at.m_begin == 1;                            // the usual case: disjoint groups
   float* o = kWrite ? out + (int64_t)p * b.n_frames * b.n_a * 3 : nullptr;
   const int n_warp = (int)min((int64_t)32, b.n_a - a_warp);                 // atoms of this warp that exist (<= 0: none)
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(128) ised_batch_kernel(IsedBatch b, const floa
     float val[3];
 #pragma unroll
     for (int pol = 0; pol < 3; ++pol) {
-      const float scaled = rescale ? __fmul_rn(fdiv(w[pol]), ml) : w[pol];
+      const float scaled = rescale ? __fmul_rn(fast_div(fdiv, w[pol]), ml) : w[pol];
       val[pol] = __fadd_rn(at.mean[pol], scaled);
     }
     float* row = o + ((int64_t)f * b.n_a + a_warp) * 3;

@@ -39,8 +39,13 @@ def effective_k_chunk(k_chunk_size: int, n_k: int) -> int:
     large as the projection scratch allows (fewer passes over the digit planes, fewer launch tails)."""
     k_chunk_size = max(1, int(k_chunk_size))
     cap = K_CHUNK_CAP if k_chunk_size >= K_CHUNK_REFERENCE_DEFAULT else k_chunk_size
-    return max(1, min(cap, n_k, K_CHUNK_CAP))
-_UPLOAD_CHUNK_BYTES = 256 << 20
+    cap = max(1, min(cap, n_k, K_CHUNK_CAP))
+    if cap < K_CHUNK_REFERENCE_DEFAULT or n_k <= cap:
+        return cap
+    # equal chunks instead of full ones plus a remainder (10 000 k: 10 x 1000, not 9 x 1024 + 784): every launch fills
+    # whole waves of projection tiles, and a streamed result ends with a chunk-sized copy instead of a long tail
+    n_chunks = -(-n_k // cap)
+    return -(-n_k // n_chunks)
 
 
 @dataclass
