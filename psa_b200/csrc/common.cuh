@@ -114,6 +114,9 @@ int launch_fft(const float* P, int64_t n_groups, int64_t group_stride, int64_t n
                int64_t n_k_total, int64_t k_offset, cudaStream_t s);
 // four-step kernel for long power-of-two columns (fft4.cu); coherent assembly only
 bool fft4_supported(int64_t n_t);
+int64_t fft4_table_entries(int64_t n_t);
+int64_t fft4_table_offset(int64_t n_t);
+int launch_fft4_tables(int64_t n_t, double2* t1, cudaStream_t s);
 int64_t fft4_workspace_bytes(int64_t n_t, int64_t n_k);
 int launch_fft4(const float* P, int64_t n_k, int64_t n_t, int64_t ldp, const void* plan, void* workspace,
                 int64_t workspace_bytes, const float* window, void* out, int64_t n_k_total, int64_t k_offset,

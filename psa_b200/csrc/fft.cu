@@ -906,6 +906,8 @@ static bool direct_length(int64_t n) { return n >= 4 && sub_length(n, nullptr) >
 
 static int64_t pass_table_entries(int64_t n_fft) { return make_passes((int)sub_length(n_fft, nullptr)).total; }
 
+int64_t fft4_table_offset(int64_t n_t) { return n_t + pass_table_entries(n_t); }   // in double2 entries from the plan start
+
 static FftGeom make_geom(int64_t n_fft, const double2* tw) {   // tw = start of the plan: [tw | pass tables | ...]
   FftGeom g;
   g.m = (int)sub_length(n_fft, &g.R);
@@ -944,7 +946,7 @@ int fft_plan_bytes(int64_t n_t, int64_t* bytes) {
     return PSA_ERR_UNSUPPORTED;
   }
   if (direct_length(n_t)) {
-    *bytes = (n_t + pass_table_entries(n_t)) * (int64_t)sizeof(double2);
+    *bytes = (n_t + pass_table_entries(n_t) + (fft4_supported(n_t) ? fft4_table_entries(n_t) : 0)) * (int64_t)sizeof(double2);
   } else {
     const int64_t M = bluestein_length(n_t);
     *bytes = (3 * M + pass_table_entries(M) + n_t) * (int64_t)sizeof(double2);
@@ -957,7 +959,10 @@ int launch_fft_plan(int64_t n_t, void* plan_buf, cudaStream_t s) {
   int st = fft_plan_bytes(n_t, &bytes);
   if (st != PSA_OK) return st;
   double2* plan = reinterpret_cast<double2*>(plan_buf);
-  if (direct_length(n_t)) return build_tables(n_t, plan, s);
+  if (direct_length(n_t)) {
+    if ((st = build_tables(n_t, plan, s)) != PSA_OK) return st;
+    return fft4_supported(n_t) ? launch_fft4_tables(n_t, plan + fft4_table_offset(n_t), s) : PSA_OK;
+  }
   const int64_t M = bluestein_length(n_t);
   double2* tw = plan;
   double2* chirp = tw + M + pass_table_entries(M);

@@ -33,6 +33,9 @@ struct Args {
   int64_t ldp;
   const float* window;
   const double2* tw;          // w_n^e, e < n (start of the FFT plan)
+  const double2* t1;          // [16][N1]: w_n^(n1 s)
+  const double2* t2;          // [N1]: w_n^(16 n1)
+  int prefetch;               // L2 prefetch of the next stage-A tile's samples
   double2* ybuf;              // RING slots of 16 columns x n
   int* counter;               // next tile
   int* done_a;                // [n_groups] stage-A tiles finished per group
@@ -108,7 +111,8 @@ __global__ void __launch_bounds__(T, OCC) fft4_kernel(Args a) {
     twb[i] = mk(w.x, w.y);
   }
   const c2* w128 = reinterpret_cast<const c2*>(c_w128);
-  const c2* tw = reinterpret_cast<const c2*>(a.tw);
+  const c2* t1 = reinterpret_cast<const c2*>(a.t1);
+  const c2* t2 = reinterpret_cast<const c2*>(a.t2);
   constexpr int TPG = G::tiles_per_group;
 
   // Tiles come from an atomic counter; the NEXT tile is taken while the current one is being processed, so the
@@ -133,7 +137,7 @@ __global__ void __launch_bounds__(T, OCC) fft4_kernel(Args a) {
           c2* y_col = reinterpret_cast<c2*>(a.ybuf) + ((int64_t)(g % a.ring) * kColsPerGroup + c_local) * G::n;
           stage_a_pass1<N1, T>(tid, n1_0, load, w128, exch);       // loads first: they do not depend on the ring slot
           __syncthreads();                                 // exchange complete; tid 0 has seen the slot free
-          stage_a_pass2<N1, T>(tid, n1_0, exch, tw, y_col);
+          stage_a_pass2<N1, T>(tid, n1_0, exch, t1, t2, y_col);
         }
         __syncthreads();                                   // every thread's Y stores precede the barrier ...
         if (tid == 0) {
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(T, OCC) fft4_kernel(Args a) {
     __syncthreads();                                       // this tile's shared-memory reads are finished; s_item is set
     item = s_item[(it + 1) & 1];
     // first touch of the next stage-A tile's samples: pull its lines into L2 while nothing depends on them yet
-    if (item < a.total_items && item % (2 * TPG) < TPG) {
+    if (a.prefetch && item < a.total_items && item % (2 * TPG) < TPG) {
       const int rn = item % (2 * TPG), gn = item / (2 * TPG);
       const int col = gn * kColsPerGroup + rn / G::a_tiles_per_column;
       if (gn < a.n_groups && col < a.n_cols) {
@@ -226,6 +230,25 @@ static Schedule make_schedule(int64_t n_t, int64_t n_cols, int sms) {
 }
 
 }  // namespace fft4
+
+// Plan layout for these lengths: [ w_n (n) | the one-CTA kernel's pass tables (incoherent assembly still uses it) |
+// t1 (16 N1) | t2 (N1) ]; fft.cu places the last two behind its own tables.
+int64_t fft4_table_entries(int64_t n_t) { return 17 * (int64_t)fft4::n1_of(n_t); }
+
+__global__ void fft4_tables_kernel(int n, int n1_len, double2* __restrict__ t1, double2* __restrict__ t2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 17 * n1_len) return;
+  const int s = i / n1_len, n1 = i % n1_len;               // s == 16: the t2 row, exponent 16 n1
+  double sn, cs;
+  sincospi(2.0 * (double)((int64_t)n1 * s) / (double)n, &sn, &cs);
+  (s < 16 ? t1 + s * n1_len : t2)[n1] = make_double2(cs, -sn);
+}
+
+int launch_fft4_tables(int64_t n_t, double2* t1, cudaStream_t s) {
+  const int n1 = fft4::n1_of(n_t);
+  fft4_tables_kernel<<<(17 * n1 + 255) / 256, 256, 0, s>>>((int)n_t, n1, t1, t1 + 16 * n1);
+  return launch_status("fft4_tables_kernel");
+}
 
 bool fft4_supported(int64_t n_t) {
   static const bool off = getenv("PSA_FFT4") != nullptr && atoi(getenv("PSA_FFT4")) == 0;
@@ -302,6 +325,10 @@ int launch_fft4(const float* P, int64_t n_k, int64_t n_t, int64_t ldp, const voi
   a.ldp = ldp;
   a.window = window;
   a.tw = reinterpret_cast<const double2*>(plan_buf);
+  a.t1 = a.tw + fft4_table_offset(n_t);
+  a.t2 = a.t1 + 16 * n1_of(n_t);
+  static const int prefetch_env = getenv("PSA_FFT4_PREFETCH") ? atoi(getenv("PSA_FFT4_PREFETCH")) : 0;
+  a.prefetch = prefetch_env;
   int* ctl = reinterpret_cast<int*>(workspace);
   a.counter = ctl;
   a.done_a = ctl + 1;

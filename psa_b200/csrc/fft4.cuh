@@ -112,7 +112,9 @@ struct Geo {
 // pass 1: x[n1 + N1 (j + 8 i)], i < 16  -> radix 16 over i -> y_s[j] * w_128^(j s)  -> exchange[s][j][l]
 // pass 2: exchange[s][0..8)[l] for s = j, j + 8 -> radix 8 over j -> k2 = 16 m + s
 //         -> * w_n^(n1 k2) -> Y[k2][n1]
-// w128: the 128 values w_128^e (constant memory on the device); tw: w_n^e, e < n.
+// w128: the 128 values w_128^e.  t1[s * N1 + n1] = w_n^(n1 s) (s < 16) and t2[n1] = w_n^(16 n1): the four-step twiddle
+// w_n^(n1 k2), k2 = 16 m + s, is t1 * t2^m; both tables are laid out so that the lanes of a warp (consecutive n1) read
+// consecutive entries.
 template <int N1, int T, class LoadF>
 F4_HD void stage_a_pass1(int tid, int n1_0, const LoadF& load, const c2* w128, c2* exch) {
   constexpr int W = Geo<N1, T>::w;
@@ -130,11 +132,11 @@ F4_HD void stage_a_pass1(int tid, int n1_0, const LoadF& load, const c2* w128, c
 }
 
 template <int N1, int T>
-F4_HD void stage_a_pass2(int tid, int n1_0, const c2* exch, const c2* tw, c2* y_col) {
+F4_HD void stage_a_pass2(int tid, int n1_0, const c2* exch, const c2* t1, const c2* t2, c2* y_col) {
   constexpr int W = Geo<N1, T>::w;
   const int lane = tid % W, warp = tid / W;
   const int n1 = n1_0 + lane;
-  const c2 step = tw[16 * n1];                               // w_n^(16 n1): from k2 to k2 + 16
+  const c2 step = t2[n1];                                    // w_n^(16 n1): from k2 to k2 + 16
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int s = warp + 8 * half;
@@ -142,7 +144,7 @@ F4_HD void stage_a_pass2(int tid, int n1_0, const c2* exch, const c2* tw, c2* y_
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = exch[(s * 8 + j) * W + lane];
     dft8(x);
-    c2 w = tw[n1 * s];                                       // w_n^(n1 s)
+    c2 w = t1[s * N1 + n1];                                  // w_n^(n1 s)
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
       y_col[(int64_t)(16 * m + s) * N1 + n1] = cmul(x[m], w);

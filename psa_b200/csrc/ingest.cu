@@ -365,7 +365,30 @@ __global__ void __launch_bounds__(512) digitize_kernel(const float* __restrict__
   }
 
   uint32_t mx[3] = {0u, 0u, 0u};
-  if (idx == nullptr) {
+  if (kStaged && idx != nullptr) {
+    // Gathered selection: the maxima pass also COMPACTS the selected atoms (mean subtracted, weight applied) into a
+    // second shared-memory array, one atom per thread (stride-3 writes: conflict-free).  The digit pass then reads
+    // whole quads as three 16-byte loads.  Gathering quads straight from the staged row put 8 lanes on one bank for
+    // the regular "every other group of four" selections of a two-sublattice crystal (ncu: 26.8 M conflicts).
+    extern __shared__ __align__(128) float s_row2[];
+    float* sel = s_row2 + ((n_a * 3 + 3) & ~(int64_t)3);
+    for (int64_t j = threadIdx.x; j < n_sel; j += blockDim.x) {
+      const int64_t atom = (int64_t)__ldg(idx + j);
+      const float wt = weight != nullptr ? __ldg(weight + atom) : 1.f;
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        float x = row[atom * 3 + p];
+        if (mean != nullptr) x = __fsub_rn(x, __ldg(mean + atom * 3 + p));
+        if (weight != nullptr) x = __fmul_rn(x, wt);
+        sel[j * 3 + p] = x;
+        mx[p] = max(mx[p], abs_bits(x));
+      }
+    }
+    row = sel;                                          // from here on: a contiguous row of n_sel atoms, ready to digitise
+    mean = nullptr;
+    weight = nullptr;
+    idx = nullptr;
+  } else if (idx == nullptr) {
     for (int64_t j0 = (int64_t)threadIdx.x * 4; j0 < n_sel; j0 += (int64_t)blockDim.x * 4) {
       float v[12];
       load_quad<kStaged>(row, mean, weight, idx, j0, n_sel, v);
@@ -425,17 +448,20 @@ __global__ void __launch_bounds__(512) digitize_kernel(const float* __restrict__
   }
 }
 
-// Long rows (more atoms than one CTA's shared memory holds, e.g. 64 000 atoms = 768 KB per frame): the two-pass
-// kernel above re-reads the row from HBM for the digit pass (ncu on C5: 75 GB of traffic for 50 GB of work).
-// Here a cluster of 8 CTAs owns one frame: each CTA fetches its share of the row with one bulk copy
-// and keeps it in shared memory, the per-polarisation maxima are exchanged through distributed shared memory,
-// and the digits are produced from the staged copy - the frame is read from HBM exactly once.
+// Contiguous rows (no gather list): a cluster of C = 1, 2, 4 or 8 CTAs owns one frame.  Each CTA fetches its share of
+// the row (<= 100 KB, two CTAs per SM) with bulk copies into shared memory and produces the digits from the staged
+// copy, so the frame is read from HBM exactly once; the per-polarisation maxima of the CTAs are exchanged through
+// distributed shared memory.  The share arrives as kDigChunks bulk copies with their own mbarriers: the maxima pass
+// starts on the first quarter while the rest is still in flight (waiting for the whole 96 KB slice of a 64 000-atom
+// frame held the kernel at 67 % of the HBM roofline).
+constexpr int kDigChunks = 4;
+
 __global__ void __launch_bounds__(256)
 digitize_cluster_kernel(const float* __restrict__ data, const float* __restrict__ mean,
                         const float* __restrict__ weight, int64_t n_t, int64_t n_a,
                         int64_t pitch, int slice_atoms, DigDests dst, int64_t t0) {
   extern __shared__ __align__(128) float s_row[];     // this CTA's slice of the frame
-  __shared__ uint64_t row_bar;
+  __shared__ uint64_t row_bar[kDigChunks];
   __shared__ uint32_t s_max[3][8], s_loc[3];
   uint32_t rank, kDigCluster;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -443,27 +469,36 @@ digitize_cluster_kernel(const float* __restrict__ data, const float* __restrict_
   const int64_t frame = blockIdx.x / kDigCluster, t = t0 + frame;
   const int64_t a0 = (int64_t)rank * slice_atoms;
   const int n_loc = (int)max((int64_t)0, min(n_a, a0 + slice_atoms) - a0);     // multiple of 4, > 0
-  const uint32_t bytes = (uint32_t)n_loc * 3 * sizeof(float);
+  const int chunk_atoms = ((n_loc + kDigChunks - 1) / kDigChunks + 3) / 4 * 4;  // whole quads: 48-byte multiples
   if (threadIdx.x == 0) {
-    mbar_init(&row_bar, 1);
+    for (int c = 0; c < kDigChunks; ++c) mbar_init(&row_bar[c], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(&row_bar, bytes);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_addr(s_row)),
-                 "l"(data + (frame * n_a + a0) * 3), "r"(bytes), "r"(smem_addr(&row_bar))
-                 : "memory");
+    const float* src = data + (frame * n_a + a0) * 3;
+    for (int c = 0; c < kDigChunks; ++c) {
+      const int c0 = min(c * chunk_atoms, n_loc), c1 = min(c0 + chunk_atoms, n_loc);
+      const uint32_t bytes = (uint32_t)(c1 - c0) * 3 * sizeof(float);
+      mbar_expect_tx(&row_bar[c], bytes);
+      if (bytes)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_addr(s_row + (size_t)c0 * 3)),
+                     "l"(src + (size_t)c0 * 3), "r"(bytes), "r"(smem_addr(&row_bar[c]))
+                     : "memory");
+    }
   }
   __syncthreads();
-  mbar_wait(&row_bar, 0);
   const float* lmean = mean != nullptr ? mean + a0 * 3 : nullptr;
   const float* lweight = weight != nullptr ? weight + a0 : nullptr;
 
   uint32_t mx[3] = {0u, 0u, 0u};
-  for (int j0 = threadIdx.x * 4; j0 < n_loc; j0 += blockDim.x * 4) {
-    float v[12];
-    load_quad<true>(s_row, lmean, lweight, nullptr, j0, n_loc, v);
+  for (int c = 0; c < kDigChunks; ++c) {
+    const int c0 = min(c * chunk_atoms, n_loc), c1 = min(c0 + chunk_atoms, n_loc);
+    mbar_wait(&row_bar[c], 0);
+    for (int j0 = c0 + threadIdx.x * 4; j0 < c1; j0 += blockDim.x * 4) {
+      float v[12];
+      load_quad<true>(s_row, lmean, lweight, nullptr, j0, n_loc, v);
 #pragma unroll
-    for (int i = 0; i < 12; ++i) mx[i % 3] = max(mx[i % 3], abs_bits(v[i]));
+      for (int i = 0; i < 12; ++i) mx[i % 3] = max(mx[i % 3], abs_bits(v[i]));
+    }
   }
 #pragma unroll
   for (int p = 0; p < 3; ++p) {
@@ -535,22 +570,21 @@ int launch_digitize_rows(const float* data, const float* mean, const float* weig
   static const bool no_stage = getenv("PSA_DIGITIZE_NO_STAGE") != nullptr;
   if (idx != nullptr && !no_stage && row_bytes <= 100 * 1024 && row_bytes % 16 == 0 &&
       (reinterpret_cast<uintptr_t>(data) & 15) == 0) {            // gathered selection, row fits: stage it
-    PSA_CUDA(cudaFuncSetAttribute(digitize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_bytes));
-    digitize_kernel<true><<<(unsigned)n_rows, 256, row_bytes, s>>>(data, mean, weight, idx, n_t_total, n_a, n_sel, pitch,
+    const size_t staged_bytes = ((row_bytes + 15) & ~(size_t)15) + (size_t)((n_sel + 3) / 4 * 4) * 3 * sizeof(float);
+    PSA_CUDA(cudaFuncSetAttribute(digitize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_bytes));
+    digitize_kernel<true><<<(unsigned)n_rows, 256, staged_bytes, s>>>(data, mean, weight, idx, n_t_total, n_a, n_sel, pitch,
                                                                      dst, t0);
     return launch_status("digitize_kernel<staged>");
   }
-  if (idx == nullptr && !no_stage && row_bytes > 200 * 1024 && n_a % 4 == 0 && (reinterpret_cast<uintptr_t>(data) & 15) == 0) {
-    // 8 CTAs with <= 100 KB slices (two clusters' CTAs per SM).  16-CTA clusters with 48 KB slices were measured
-    // slower (scripts/digitize_tune.py, 64 000 atoms: 4.0 vs 4.7 TB/s); PSA_DIG_CLUSTER=16 selects them for A/B runs.
-    static const int forced = getenv("PSA_DIG_CLUSTER") ? atoi(getenv("PSA_DIG_CLUSTER")) : 8;
-    for (int C : {16, 8}) {
-      if (C != forced) continue;
+  if (idx == nullptr && !no_stage && n_a % 4 == 0 && n_a >= 64 && (reinterpret_cast<uintptr_t>(data) & 15) == 0) {
+    // smallest cluster whose slices fit two CTAs per SM (<= 100 KB each): 1 for 4096 atoms, 2 for 13 824, 8 for 64 000
+    static const int forced = getenv("PSA_DIG_CLUSTER") ? atoi(getenv("PSA_DIG_CLUSTER")) : 0;
+    for (int C : {1, 2, 4, 8}) {
+      if (forced && C != forced) continue;
       const int slice_atoms = (int)(((n_a + C - 1) / C + 3) / 4 * 4);
       const size_t slice_bytes = (size_t)slice_atoms * 3 * sizeof(float);
-      if (slice_bytes > (C == 16 ? 52u : 100u) * 1024 || (int64_t)slice_atoms * (C - 1) >= n_a) continue;
+      if (slice_bytes > 100u * 1024 || (int64_t)slice_atoms * (C - 1) >= n_a) continue;
       PSA_CUDA(cudaFuncSetAttribute(digitize_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice_bytes));
-      PSA_CUDA(cudaFuncSetAttribute(digitize_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)(n_rows * C));
       cfg.blockDim = dim3(256);

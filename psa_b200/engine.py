@@ -30,6 +30,7 @@ from . import _lib
 
 K_CHUNK_CAP = 1024            # k-points per chunk (2048 projection rows = 16 row tiles)
 K_CHUNK_REFERENCE_DEFAULT = 500   # the reference's default k_chunk_size (sed_calculator.py:185)
+_UPLOAD_CHUNK_BYTES = 256 << 20   # pinned staging buffers for uploads from pageable / memory-mapped arrays
 
 
 def effective_k_chunk(k_chunk_size: int, n_k: int) -> int:

@@ -37,11 +37,15 @@ static double run() {
   typedef Geo<N1, T> G;
   const int kThreads = T, kN1Tile = G::w;
   const int n = G::n, cols = kColsPerGroup;
-  std::vector<c2> w128(128), tw(n), twb(G::q * 17);
+  std::vector<c2> w128(128), tw(n), twb(G::q * 17), t1(16 * N1), t2(N1);
   for (int e = 0; e < 128; ++e) w128[e] = mk(std::cos(-2 * M_PI * e / 128.0), std::sin(-2 * M_PI * e / 128.0));
   for (int e = 0; e < n; ++e) tw[e] = mk(std::cos(-2 * M_PI * e / (double)n), std::sin(-2 * M_PI * e / (double)n));
   for (int j = 0; j < G::q; ++j)
     for (int s = 0; s < 16; ++s) twb[j * 17 + s] = tw[kN2 * j * s];
+  for (int n1 = 0; n1 < N1; ++n1) {
+    t2[n1] = tw[16 * n1];
+    for (int s = 0; s < 16; ++s) t1[s * N1 + n1] = tw[n1 * s];
+  }
   std::vector<std::vector<cplx>> x(cols, std::vector<cplx>(n));
   srand(N1);
   for (int c = 0; c < cols; ++c)
@@ -55,7 +59,7 @@ static double run() {
       const int n1_0 = tile * kN1Tile;
       auto load = [&](int t) { return mk(x[c][t].real(), x[c][t].imag()); };
       for (int tid = 0; tid < kThreads; ++tid) stage_a_pass1<N1, T>(tid, n1_0, load, w128.data(), exch.data());
-      for (int tid = 0; tid < kThreads; ++tid) stage_a_pass2<N1, T>(tid, n1_0, exch.data(), tw.data(), y.data() + (size_t)c * n);
+      for (int tid = 0; tid < kThreads; ++tid) stage_a_pass2<N1, T>(tid, n1_0, exch.data(), t1.data(), t2.data(), y.data() + (size_t)c * n);
     }
   // stage B: every k2 tile of the group
   std::vector<std::vector<cplx>> got(cols, std::vector<cplx>(n));
