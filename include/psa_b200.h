@@ -152,7 +152,7 @@ int psa_intensity(const float* sed, int64_t n_rows, int n_pol, float* out, void*
  *                    numeric factor: div = 1, mul = factor (:527); div = mul = 1 leaves w untouched.
  *   mean [n_a][3] float32   khat [3] float32   k_act [n_points] float32   amp [n_points][n_groups][3] complex64
  *   member_off [n_a + 1], member_grp: CSR list of the groups each atom belongs to (ascending; empty = atom keeps
- *   its mean position)                     out [n_points][n_frames][n_a][3] float32, n_frames <= 1024
+ *   its mean position)                     out [n_points][n_frames][n_a][3] float32, n_frames <= 65536
  * psa_ised_absmax: wmax[p] = max over frames, polarisations and the atoms of every group of |w after that group|
  *   (the reference's running max_wiggle_amp_all, :502-504); stores nothing else. */
 int psa_ised_absmax(const float* mean, const float* khat, const float* k_act, const float* amp,

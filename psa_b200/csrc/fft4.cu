@@ -94,8 +94,8 @@ struct StoreOut {
 };
 
 // OCC = CTAs per SM the register allocation is capped for: the butterflies hold 16 complex128 values (64 registers)
-// and ptxas fits the whole tile loop in 80 registers with a few bytes of spill, so six 128-thread CTAs (24 warps,
-// six independent tile phases) share an SM.
+// and ptxas fits the whole tile loop in 80-96 registers with a few bytes of spill.  Five 128-thread CTAs per SM
+// measured best (more CTAs shrink the L1 next to their shared memory; fewer leave latency exposed).
 template <int N1, int T, int OCC>
 __global__ void __launch_bounds__(T, OCC) fft4_kernel(Args a) {
   using G = Geo<N1, T>;
@@ -189,8 +189,8 @@ static int n1_of(int64_t n_t) {
 template <int N1, int T>
 static size_t smem_bytes() { return (size_t)(Geo<N1, T>::exchange_elems + Geo<N1, T>::q * 17) * sizeof(double2); }
 
-// threads per CTA: 128 where a 2048-point stage-B tile still spans 16 columns, else 256; CTAs per SM: 6 x 128 or
-// 3 x 256 threads (PSA_FFT4_THREADS / PSA_FFT4_OCC select the other compiled variants for A/B runs)
+// threads per CTA: 128 where a 2048-point stage-B tile still spans 16 columns, else 256; CTAs per SM: 5 x 128 or
+// 2 x 256 threads (PSA_FFT4_THREADS / PSA_FFT4_OCC select the other compiled variants for A/B runs)
 static int threads_of(int n1) {
   static const int forced = getenv("PSA_FFT4_THREADS") ? atoi(getenv("PSA_FFT4_THREADS")) : 0;
   if (n1 == 256) return 256;
@@ -198,8 +198,8 @@ static int threads_of(int n1) {
 }
 static int occ_of(int threads) {
   static const int forced = getenv("PSA_FFT4_OCC") ? atoi(getenv("PSA_FFT4_OCC")) : 0;
-  if (threads == 128) return (forced == 4 || forced == 5) ? forced : 6;
-  return forced == 2 ? 2 : 3;
+  if (threads == 128) return (forced == 4 || forced == 6) ? forced : 5;     // 16384 x 1024 k: 0.431 / 0.404 / 0.490 ms for 4 / 5 / 6
+  return forced == 3 ? 3 : 2;                                               // 32768 x 256 k: 0.247 / 0.266 ms for 2 / 3
 }
 
 struct Schedule {

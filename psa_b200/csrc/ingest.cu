@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(512) digitize_kernel(const float* __restrict__
                                                        const float* __restrict__ weight,
                                                        const int32_t* __restrict__ idx, int64_t n_t,
                                                        int64_t n_a, int64_t n_sel, int64_t pitch,
-                                                       DigDests dst, int64_t t0) {
+                                                       DigDests dst, int64_t t0, bool compact) {
   // `data` holds the rows [t0, t0 + gridDim.x) of a trajectory of n_t frames; dig / expo describe all n_t frames
   const int64_t t = t0 + blockIdx.x;
   const float* row = data + (int64_t)blockIdx.x * n_a * 3;
@@ -365,8 +365,9 @@ __global__ void __launch_bounds__(512) digitize_kernel(const float* __restrict__
   }
 
   uint32_t mx[3] = {0u, 0u, 0u};
-  if (kStaged && idx != nullptr) {
-    // Gathered selection: the maxima pass also COMPACTS the selected atoms (mean subtracted, weight applied) into a
+  if (kStaged && idx != nullptr && compact) {
+    // Gathered selection (PSA_DIG_COMPACT=1; measured 6 % slower than gathering twice, so off by default - the bank
+    // conflicts it removes were not what bounds the kernel): the maxima pass also COMPACTS the selected atoms (mean subtracted, weight applied) into a
     // second shared-memory array, one atom per thread (stride-3 writes: conflict-free).  The digit pass then reads
     // whole quads as three 16-byte loads.  Gathering quads straight from the staged row put 8 lanes on one bank for
     // the regular "every other group of four" selections of a two-sublattice crystal (ncu: 26.8 M conflicts).
@@ -570,15 +571,20 @@ int launch_digitize_rows(const float* data, const float* mean, const float* weig
   static const bool no_stage = getenv("PSA_DIGITIZE_NO_STAGE") != nullptr;
   if (idx != nullptr && !no_stage && row_bytes <= 100 * 1024 && row_bytes % 16 == 0 &&
       (reinterpret_cast<uintptr_t>(data) & 15) == 0) {            // gathered selection, row fits: stage it
-    const size_t staged_bytes = ((row_bytes + 15) & ~(size_t)15) + (size_t)((n_sel + 3) / 4 * 4) * 3 * sizeof(float);
+    static const bool compact = getenv("PSA_DIG_COMPACT") != nullptr && atoi(getenv("PSA_DIG_COMPACT")) != 0;
+    const size_t staged_bytes = ((row_bytes + 15) & ~(size_t)15) + (compact ? (size_t)((n_sel + 3) / 4 * 4) * 3 * sizeof(float) : 0);
     PSA_CUDA(cudaFuncSetAttribute(digitize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_bytes));
     digitize_kernel<true><<<(unsigned)n_rows, 256, staged_bytes, s>>>(data, mean, weight, idx, n_t_total, n_a, n_sel, pitch,
-                                                                     dst, t0);
+                                                                     dst, t0, compact);
     return launch_status("digitize_kernel<staged>");
   }
-  if (idx == nullptr && !no_stage && n_a % 4 == 0 && n_a >= 64 && (reinterpret_cast<uintptr_t>(data) & 15) == 0) {
-    // smallest cluster whose slices fit two CTAs per SM (<= 100 KB each): 1 for 4096 atoms, 2 for 13 824, 8 for 64 000
-    static const int forced = getenv("PSA_DIG_CLUSTER") ? atoi(getenv("PSA_DIG_CLUSTER")) : 0;
+  // Rows longer than 200 KB (64 000 atoms: 768 KB) take the cluster kernel - the two-pass kernel below would read them
+  // from HBM twice.  Shorter rows stay in L1/L2 between the two passes of the plain kernel, which measured faster than
+  // staging them (13 824 atoms: 1.07 vs 1.16 ms; 4096 atoms: equal); PSA_DIG_CLUSTER=1|2|4|8 forces a cluster size.
+  static const int forced_cluster = getenv("PSA_DIG_CLUSTER") ? atoi(getenv("PSA_DIG_CLUSTER")) : 0;
+  if (idx == nullptr && !no_stage && n_a % 4 == 0 && n_a >= 64 && (reinterpret_cast<uintptr_t>(data) & 15) == 0 &&
+      (row_bytes > 200 * 1024 || forced_cluster)) {
+    const int forced = forced_cluster;
     for (int C : {1, 2, 4, 8}) {
       if (forced && C != forced) continue;
       const int slice_atoms = (int)(((n_a + C - 1) / C + 3) / 4 * 4);
@@ -604,7 +610,7 @@ int launch_digitize_rows(const float* data, const float* mean, const float* weig
   }
   // 512 threads for contiguous rows, 256 for gathered ones (bench.py on C1 / C2: 0.131 vs 0.142 ms, 0.242 vs 0.252 ms)
   digitize_kernel<false><<<(unsigned)n_rows, idx == nullptr ? 512 : 256, 0, s>>>(data, mean, weight, idx, n_t_total, n_a,
-                                                                                   n_sel, pitch, dst, t0);
+                                                                                   n_sel, pitch, dst, t0, false);
   return launch_status("digitize_kernel");
 }
 

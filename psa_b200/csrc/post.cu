@@ -85,13 +85,15 @@ int launch_intensity(const float2* sed, int64_t n_rows, int n_pol, float* out, c
 // 12 bytes it writes per (point, frame, atom).  A thread owns one atom of one point and walks the frames;
 // the groups an atom belongs to come as a CSR list in processing order (atoms in no group keep the mean).
 // ---------------------------------------------------------------------------------------------
-constexpr int kIsedMaxFrames = 1024;            // phasor table C_f, S_f in shared memory
+constexpr int kIsedMaxFrames = 65536;           // frames of one reconstruction (grid z = frames / 32)
 
-__device__ __forceinline__ void ised_fill_phasors(double2* tab, int n_frames) {
-  for (int f = threadIdx.x; f < n_frames; f += blockDim.x) {
+constexpr int kIsedFrameChunk = 32;             // frames per block (grid z): small blocks keep the last wave short
+
+__device__ __forceinline__ void ised_fill_phasors(double2* tab, int f_begin, int f_end, int n_frames) {
+  for (int f = f_begin + threadIdx.x; f < f_end; f += blockDim.x) {
     double s, c;
     sincos(6.283185307179586 * (double)f / (double)n_frames, &s, &c);   // np.linspace(0, 2 pi, n, endpoint=False)
-    tab[f] = make_double2(c, s);
+    tab[f - f_begin] = make_double2(c, s);
   }
 }
 
@@ -166,9 +168,10 @@ template <bool kWrite, bool kWide>
 __global__ void __launch_bounds__(128) ised_batch_kernel(IsedBatch b, const float* __restrict__ div,
                                                          const float* __restrict__ mul, float* __restrict__ out,
                                                          float* __restrict__ wmax) {
-  __shared__ double2 phasor[kIsedMaxFrames];
+  __shared__ double2 phasor[kIsedFrameChunk];
   __shared__ __align__(16) float stage[4][2][96];          // [warp][double buffer][32 atoms x 3]
-  ised_fill_phasors(phasor, b.n_frames);
+  const int f_begin = blockIdx.z * kIsedFrameChunk, f_end = min(b.n_frames, f_begin + kIsedFrameChunk);
+  ised_fill_phasors(phasor, f_begin, f_end, b.n_frames);
   __syncthreads();
   const int p = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -193,8 +196,8 @@ __global__ void __launch_bounds__(128) ised_batch_kernel(IsedBatch b, const floa
   const bool single = at.m_end - at.m_begin == 1;                            // the usual case: disjoint groups
   float* o = kWrite ? out + (int64_t)p * b.n_frames * b.n_a * 3 : nullptr;
   const int n_warp = (int)min((int64_t)32, b.n_a - a_warp);                 // atoms of this warp that exist (<= 0: none)
-  for (int f = 0; f < b.n_frames; ++f) {
-    const double2 cs = phasor[f];
+  for (int f = f_begin; f < f_end; ++f) {
+    const double2 cs = phasor[f - f_begin];
     float w[3] = {0.f, 0.f, 0.f};
     if (live) {
       if (single) {
@@ -239,6 +242,7 @@ __global__ void __launch_bounds__(128) ised_batch_kernel(IsedBatch b, const floa
 static int ised_check(const IsedBatch& b) {
   PSA_REQUIRE(b.n_frames <= kIsedMaxFrames, "psa_ised: at most %d reconstruction frames per call (got %d)", kIsedMaxFrames,
               b.n_frames);
+  static_assert(kIsedMaxFrames / kIsedFrameChunk <= 65535, "grid z");
   PSA_REQUIRE(b.n_points <= 65535, "psa_ised: at most 65535 points per call");
   return PSA_OK;
 }
@@ -248,7 +252,7 @@ int launch_ised_absmax(const IsedBatch& b, float* wmax, cudaStream_t s) {
   if (st != PSA_OK) return st;
   PSA_CUDA(cudaMemsetAsync(wmax, 0, sizeof(float) * (size_t)(b.n_points > 0 ? b.n_points : 0), s));
   if (b.n_a == 0 || b.n_frames == 0 || b.n_points == 0) return PSA_OK;
-  dim3 grid((unsigned)((b.n_a + 127) / 128), (unsigned)b.n_points);
+  dim3 grid((unsigned)((b.n_a + 127) / 128), (unsigned)b.n_points, (unsigned)((b.n_frames + kIsedFrameChunk - 1) / kIsedFrameChunk));
   ised_batch_kernel<false, false><<<grid, 128, 0, s>>>(b, nullptr, nullptr, nullptr, wmax);
   return launch_status("ised_batch_kernel<max>");
 }
@@ -257,7 +261,7 @@ int launch_ised_frames(const IsedBatch& b, const float* div, const float* mul, f
   int st = ised_check(b);
   if (st != PSA_OK) return st;
   if (b.n_a == 0 || b.n_frames == 0 || b.n_points == 0) return PSA_OK;
-  dim3 grid((unsigned)((b.n_a + 127) / 128), (unsigned)b.n_points);
+  dim3 grid((unsigned)((b.n_a + 127) / 128), (unsigned)b.n_points, (unsigned)((b.n_frames + kIsedFrameChunk - 1) / kIsedFrameChunk));
   if (b.n_a % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
     ised_batch_kernel<true, true><<<grid, 128, 0, s>>>(b, div, mul, out, nullptr);
   else
