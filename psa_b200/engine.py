@@ -28,7 +28,8 @@ import torch
 
 from . import _lib
 
-K_CHUNK_CAP = 1024            # k-points per chunk (2048 projection rows = 16 row tiles)
+# k-points per chunk (at most 1024 = 2048 projection rows = 16 row tiles); PSA_B200_K_CHUNK lowers it for A/B runs
+K_CHUNK_CAP = max(8, min(1024, int(os.environ.get("PSA_B200_K_CHUNK", "1024"))))
 K_CHUNK_REFERENCE_DEFAULT = 500   # the reference's default k_chunk_size (sed_calculator.py:185)
 _UPLOAD_CHUNK_BYTES = 256 << 20   # pinned staging buffers for uploads from pageable / memory-mapped arrays
 

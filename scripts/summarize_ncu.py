@@ -76,7 +76,8 @@ def full(src, dst, workload=None):
             return {"mean_positions_kernel": "psa_mean_positions", "mean_positions_tma_kernel": "psa_mean_positions",
                     "digitize_kernel": "psa_digitize", "phase_digits_kernel": "psa_phase_digits",
                     "project_tc_kernel": "psa_project", "project_tc2_kernel": "psa_project",
-                    "fft_sed_kernel": "psa_fft_sed"}.get(base, kernel)
+                    "fft_sed_kernel": "psa_fft_sed", "fft4_kernel": "psa_fft_sed", "digitize_cluster_kernel": "psa_digitize",
+                    "ised_batch_kernel": "psa_ised_frames"}.get(base, kernel)
         api = {k: api_name(k) for k in traffic}
         p = Path(dst).parent / "ncu_traffic.json"
         data = json.loads(p.read_text()) if p.exists() else {}

