@@ -82,11 +82,14 @@ int psa_digitize_rows(const float* data, const float* mean, const float* weight,
  * its own frames straight into every rank's planes through NVLink - the all-gather that would follow
  * (the one exchange step of the k-sharded path) is fused into the producing kernel.
  *   dig_all_host / expo_all_host: HOST arrays of n_dst (<= 8) device pointers, each laid out like dig / expo above.
+ *   light != 0: small-footprint launch (128-thread CTAs, no shared-memory staging) that fits on the SMs next to a
+ *   running psa_project - the ring steps of a pipelined exchange run under the first k-chunk's projection.
  * The caller orders the ranks around the call (nobody still reads the previous planes; everybody has finished
  * writing before anyone projects). */
 int psa_digitize_rows_peers(const float* data, const float* mean, const float* weight, const int32_t* idx, int64_t n_rows,
                             int64_t n_atoms, int64_t n_sel, int64_t pitch, void* const* dig_all_host,
-                            void* const* expo_all_host, int64_t n_dst, int64_t n_t_total, int64_t t0, void* stream);
+                            void* const* expo_all_host, int64_t n_dst, int64_t n_t_total, int64_t t0, int light,
+                            void* stream);
 
 /* CUDA IPC plumbing for the above (one process per GPU, same box):
  *   psa_ipc_export: 64-byte handle of the allocation that contains `ptr` + the offset of `ptr` inside it (host outputs)
@@ -110,6 +113,14 @@ int psa_phase_digits(const float* kvecs, int64_t n_k, const float* mean, const i
 int psa_project(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig,
                 const int32_t* expo, int64_t n_t, int64_t n_sel, int64_t pitch, float* P, int64_t ldp,
                 int impl, void* stream);
+
+/* The same for the frames [t0, t0 + n_t_rows) only (all rows, all polarisations): bdig / expo / P are the full-size
+ * buffers of an n_t-frame trajectory.  Every (row, frame) of P is an independent exact sum, so projecting a
+ * trajectory range by range gives the bits of one call; a multi-GPU sliced ingest uses this to start projecting the
+ * frames that have already arrived from a peer while the next peer's rows are still crossing NVLink. */
+int psa_project_rows(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig, const int32_t* expo,
+                     int64_t n_t, int64_t t0, int64_t n_t_rows, int64_t n_sel, int64_t pitch, float* P, int64_t ldp,
+                     int impl, void* stream);
 
 /* FFT plan for n_t frames: twiddles, plus (when n_t is not a power of two) the Bluestein chirp and
  * its spectrum.  The caller owns the buffer: allocate psa_fft_plan_bytes(n_t) device bytes (-1 = n_t not

@@ -37,6 +37,8 @@ _SIGNATURES = {
                                  c_void_p, c_void_p]),
     "psa_project": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                             c_void_p, c_int64, c_int, c_void_p]),
+    "psa_project_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                 c_void_p, c_int64, c_int, c_void_p]),
     "psa_fft_plan_bytes": (c_int64, [c_int64]),
     "psa_fft_plan_init": (c_int, [c_int64, c_void_p, c_void_p]),
     "psa_fft_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
@@ -59,7 +61,7 @@ _SIGNATURES = {
                                   c_void_p, c_int64, c_int64, c_void_p]),
     "psa_copy_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "psa_digitize_rows_peers": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p,
-                                        c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+                                        c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "psa_write_dump": (c_int, [c_char_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int]),
     "psa_host_register": (c_int, [c_void_p, c_int64]),
     "psa_host_unregister": (c_int, [c_void_p]),

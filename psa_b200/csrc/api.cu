@@ -89,7 +89,8 @@ int psa_digitize_rows(const float* data, const float* mean, const float* weight,
 
 int psa_digitize_rows_peers(const float* data, const float* mean, const float* weight, const int32_t* idx, int64_t n_rows,
                             int64_t n_a, int64_t n_sel, int64_t pitch, void* const* dig_all_host,
-                            void* const* expo_all_host, int64_t n_dst, int64_t n_t_total, int64_t t0, void* stream) {
+                            void* const* expo_all_host, int64_t n_dst, int64_t n_t_total, int64_t t0, int light,
+                            void* stream) {
   PSA_REQUIRE(dig_all_host && expo_all_host && (data || n_rows == 0), "psa_digitize_rows_peers: null pointer");
   PSA_REQUIRE(n_dst >= 1 && n_dst <= kMaxPeers, "psa_digitize_rows_peers: between 1 and %d destinations (got %lld)",
               kMaxPeers, (long long)n_dst);
@@ -105,7 +106,8 @@ int psa_digitize_rows_peers(const float* data, const float* mean, const float* w
     dst.dig[d] = reinterpret_cast<int8_t*>(dig_all_host[d]);
     dst.expo[d] = reinterpret_cast<int32_t*>(expo_all_host[d]);
   }
-  return launch_digitize_rows(data, mean, weight, idx, n_rows, n_a, n_sel, pitch, dst, n_t_total, t0, as_stream(stream));
+  return launch_digitize_rows(data, mean, weight, idx, n_rows, n_a, n_sel, pitch, dst, n_t_total, t0, as_stream(stream),
+                              light != 0);
 }
 
 // ---- page-locking of caller-owned host memory (a result array shared by the ranks of one box)
@@ -180,21 +182,33 @@ int psa_phase_digits(const float* kvecs, int64_t n_k, const float* mean, const i
   return launch_phase_digits(kvecs, n_k, mean, idx, n_sel, pitch, rows_alloc, adig, as_stream(stream));
 }
 
-int psa_project(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig, const int32_t* expo,
-                int64_t n_t, int64_t n_sel, int64_t pitch, float* P, int64_t ldp, int impl, void* stream) {
+int psa_project_rows(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig, const int32_t* expo,
+                     int64_t n_t, int64_t t0, int64_t n_t_rows, int64_t n_sel, int64_t pitch, float* P, int64_t ldp,
+                     int impl, void* stream) {
   PSA_REQUIRE(adig && bdig && expo && P, "psa_project: null pointer");
   PSA_REQUIRE(rows > 0 && rows <= rows_alloc && n_t > 0 && n_sel > 0, "psa_project: bad extents");
+  PSA_REQUIRE(t0 >= 0 && n_t_rows >= 0 && t0 + n_t_rows <= n_t, "psa_project: frame range [%lld, %lld) outside %lld frames",
+              (long long)t0, (long long)(t0 + n_t_rows), (long long)n_t);
   PSA_REQUIRE(pitch >= n_sel && pitch % 64 == 0, "psa_project: pitch must be a multiple of 64 and >= n_sel");
   PSA_REQUIRE(ldp >= n_t && ldp % 4 == 0, "psa_project: ldp must be a multiple of 4 and >= n_t");
   PSA_REQUIRE(((uintptr_t)adig % 16) == 0 && ((uintptr_t)bdig % 16) == 0 && ((uintptr_t)P % 16) == 0,
               "psa_project: buffers must be 16-byte aligned");
+  if (n_t_rows == 0) return PSA_OK;
   DeviceGuard guard(P);
+  const int8_t* b0 = bdig + t0 * pitch;
+  const int32_t* e0 = expo + t0;
+  float* p0 = P + t0;
   if (impl == PSA_PROJECT_TENSOR)
-    return launch_project_tc2(adig, rows, rows_alloc, bdig, expo, n_t, n_sel, pitch, P, ldp, as_stream(stream));
+    return launch_project_tc2(adig, rows, rows_alloc, b0, e0, n_t_rows, n_t, n_sel, pitch, p0, ldp, as_stream(stream));
   if (impl == PSA_PROJECT_SIMT)
-    return launch_project_simt(adig, rows, rows_alloc, bdig, expo, n_t, n_sel, pitch, P, ldp, as_stream(stream));
+    return launch_project_simt(adig, rows, rows_alloc, b0, e0, n_t_rows, n_t, n_sel, pitch, p0, ldp, as_stream(stream));
   set_error("psa_project: unknown impl %d", impl);
   return PSA_ERR_BAD_ARG;
+}
+
+int psa_project(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig, const int32_t* expo,
+                int64_t n_t, int64_t n_sel, int64_t pitch, float* P, int64_t ldp, int impl, void* stream) {
+  return psa_project_rows(adig, rows, rows_alloc, bdig, expo, n_t, 0, n_t, n_sel, pitch, P, ldp, impl, stream);
 }
 
 int64_t psa_fft_plan_bytes(int64_t n_t) {

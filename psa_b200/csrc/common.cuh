@@ -95,16 +95,16 @@ struct DigDests {
 };
 int launch_digitize_rows(const float* data, const float* mean, const float* weight, const int32_t* idx, int64_t n_rows,
                          int64_t n_a, int64_t n_sel, int64_t pitch, const DigDests& dst, int64_t n_t_total, int64_t t0,
-                         cudaStream_t s);
+                         cudaStream_t s, bool light = false);
 int launch_digitize(const float* data, const float* mean, const float* weight, const int32_t* idx, int64_t n_t,
                     int64_t n_a, int64_t n_sel, int64_t pitch, int8_t* dig, int32_t* expo, cudaStream_t s);
 int launch_phase_digits(const float* kvecs, int64_t n_k, const float* mean, const int32_t* idx,
                         int64_t n_sel, int64_t pitch, int64_t rows_alloc, int8_t* adig, cudaStream_t s);
 int launch_project_tc2(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig,
-                       const int32_t* expo, int64_t n_t, int64_t n_sel, int64_t pitch, float* P,
+                       const int32_t* expo, int64_t n_t, int64_t n_t_total, int64_t n_sel, int64_t pitch, float* P,
                        int64_t ldp, cudaStream_t s);
 int launch_project_simt(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig,
-                        const int32_t* expo, int64_t n_t, int64_t n_sel, int64_t pitch, float* P,
+                        const int32_t* expo, int64_t n_t, int64_t n_t_total, int64_t n_sel, int64_t pitch, float* P,
                         int64_t ldp, cudaStream_t s);
 int fft_plan_bytes(int64_t n_t, int64_t* bytes);
 int fft_workspace_bytes(int64_t n_t, int64_t n_k, int64_t n_groups, int64_t* bytes);

@@ -559,14 +559,22 @@ int launch_digitize(const float* data, const float* mean, const float* weight, c
   dst.n = 1;
   dst.dig[0] = dig;
   dst.expo[0] = expo;
-  return launch_digitize_rows(data, mean, weight, idx, n_t, n_a, n_sel, pitch, dst, n_t, 0, s);
+  return launch_digitize_rows(data, mean, weight, idx, n_t, n_a, n_sel, pitch, dst, n_t, 0, s, false);
 }
 
 int launch_digitize_rows(const float* data, const float* mean, const float* weight, const int32_t* idx, int64_t n_rows,
                          int64_t n_a, int64_t n_sel, int64_t pitch, const DigDests& dst, int64_t n_t_total, int64_t t0,
-                         cudaStream_t s) {
+                         cudaStream_t s, bool light) {
   if (n_rows == 0) return PSA_OK;
   DeviceGuard guard(data);
+  if (light) {
+    // A ring step of the multi-GPU exchange runs UNDER the projection kernel, which leaves 10 240 registers and
+    // ~30 KB of shared memory per SM: 128-thread CTAs of the plain two-pass kernel (64 registers, no staging) fit
+    // next to it; the row is L2-hot for the second pass and the step is NVLink-bound anyway.
+    digitize_kernel<false><<<(unsigned)n_rows, 128, 0, s>>>(data, mean, weight, idx, n_t_total, n_a, n_sel, pitch, dst, t0,
+                                                            false);
+    return launch_status("digitize_kernel<light>");
+  }
   const size_t row_bytes = (size_t)n_a * 3 * sizeof(float);
   static const bool no_stage = getenv("PSA_DIGITIZE_NO_STAGE") != nullptr;
   if (idx != nullptr && !no_stage && row_bytes <= 100 * 1024 && row_bytes % 16 == 0 &&

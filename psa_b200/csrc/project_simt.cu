@@ -11,7 +11,7 @@ constexpr int LDW = TKW + 1;                // padded row length in words
 
 __global__ void __launch_bounds__(256) project_simt_kernel(
     const int8_t* __restrict__ adig, int64_t rows, int64_t rows_alloc, const int8_t* __restrict__ bdig,
-    const int32_t* __restrict__ expo, int64_t n_t, int64_t pitch, int64_t a_begin, int64_t a_end,
+    const int32_t* __restrict__ expo, int64_t n_t, int64_t n_t_total, int64_t pitch, int64_t a_begin, int64_t a_end,
     int accumulate, float* __restrict__ P, int64_t ldp) {
   __shared__ uint32_t As[kSlices][TM][LDW];
   __shared__ uint32_t Bs[kSlices][TN][LDW];
@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) project_simt_kernel(
   const int64_t t0 = (int64_t)blockIdx.x * TN;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int64_t a_plane = rows_alloc * pitch;
-  const int64_t b_plane = n_t * pitch;
+  const int64_t b_plane = n_t_total * pitch;
 
   int32_t acc[kClasses][4][4] = {};
 
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) project_simt_kernel(
     for (int j = 0; j < 4; ++j) {
       int64_t t = t0 + tx * 4 + j;
       if (t >= n_t) continue;
-      int e = __ldg(expo + pol * n_t + t);
+      int e = __ldg(expo + pol * n_t_total + t);
       float v = combine_classes(acc[0][i][j], acc[1][i][j], acc[2][i][j], acc[3][i][j], e);
       float* dst = P + (m * 3 + pol) * ldp + t;
       *dst = accumulate ? __fadd_rn(*dst, v) : v;
@@ -82,14 +82,14 @@ __global__ void __launch_bounds__(256) project_simt_kernel(
 }
 
 int launch_project_simt(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig,
-                        const int32_t* expo, int64_t n_t, int64_t n_sel, int64_t pitch, float* P,
+                        const int32_t* expo, int64_t n_t, int64_t n_t_total, int64_t n_sel, int64_t pitch, float* P,
                         int64_t ldp, cudaStream_t s) {
   if (rows == 0 || n_t == 0) return PSA_OK;
   dim3 grid((unsigned)((n_t + TN - 1) / TN), (unsigned)((rows + TM - 1) / TM), 3);
   int pass = 0;
   for (int64_t a0 = 0; a0 < pitch && (a0 < n_sel || pass == 0); a0 += kMaxAtomsPerPass, ++pass) {
     int64_t a1 = a0 + kMaxAtomsPerPass < pitch ? a0 + kMaxAtomsPerPass : pitch;
-    project_simt_kernel<<<grid, 256, 0, s>>>(adig, rows, rows_alloc, bdig, expo, n_t, pitch, a0, a1,
+    project_simt_kernel<<<grid, 256, 0, s>>>(adig, rows, rows_alloc, bdig, expo, n_t, n_t_total, pitch, a0, a1,
                                              pass > 0, P, ldp);
     int st = launch_status("project_simt_kernel");
     if (st != PSA_OK) return st;

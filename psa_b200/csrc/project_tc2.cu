@@ -167,8 +167,8 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, int r_tiles, int t_ti
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 project_tc2_kernel(const __grid_constant__ CUtensorMap tmap_phase, const __grid_constant__ CUtensorMap tmap_traj,
-                   const int32_t* __restrict__ expo, float* __restrict__ P, int rows, int n_t, int64_t ldp,
-                   int a_begin, int a_end, int accumulate, int r_tiles, int t_tiles) {
+                   const int32_t* __restrict__ expo, float* __restrict__ P, int rows, int n_t, int64_t expo_stride,
+                   int64_t ldp, int a_begin, int a_end, int accumulate, int r_tiles, int t_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -275,7 +275,7 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tmap_phase, const __grid_
       tc_fence_after();
       const int t = tc.t_tile * 2 * BM + (int)rank * BM + quarter * 32 + lane;
       const bool t_ok = t < n_t;
-      const int e = t_ok ? __ldg(expo + (int64_t)tc.pol * n_t + t) : kExpMin;
+      const int e = t_ok ? __ldg(expo + (int64_t)tc.pol * expo_stride + t) : kExpMin;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
       const int c_begin = part * EPI_COLS, c_end = min(tc.n_cols, c_begin + EPI_COLS);
       // Drain first, store later: the accumulators are read and recombined into EPI_COLS float32 values
@@ -354,9 +354,10 @@ static int make_map(CUtensorMap* map, const int8_t* base, int64_t n_sel, int64_t
 
 }  // namespace tc2
 
+// bdig / expo / P point at the first frame of the range to project; n_t frames of a trajectory of n_t_total frames
 int launch_project_tc2(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig,
-                       const int32_t* expo, int64_t n_t, int64_t n_sel, int64_t pitch, float* P, int64_t ldp,
-                       cudaStream_t s) {
+                       const int32_t* expo, int64_t n_t, int64_t n_t_total, int64_t n_sel, int64_t pitch, float* P,
+                       int64_t ldp, cudaStream_t s) {
   using namespace tc2;
   if (rows == 0 || n_t == 0) return PSA_OK;
   DeviceGuard guard(P);
@@ -365,7 +366,7 @@ int launch_project_tc2(const int8_t* adig, int64_t rows, int64_t rows_alloc, con
   CUtensorMap map_phase, map_traj;
   int st = make_map(&map_phase, adig, n_sel, pitch, rows, rows_alloc, kSlices, BNH);
   if (st != PSA_OK) return st;
-  st = make_map(&map_traj, bdig, n_sel, pitch, n_t, n_t, 3 * kSlices, BM);
+  st = make_map(&map_traj, bdig, n_sel, pitch, n_t, n_t_total, 3 * kSlices, BM);
   if (st != PSA_OK) return st;
 
   // per device and per context: set on every launch (a process may drive several GPUs from several threads)
@@ -381,7 +382,7 @@ int launch_project_tc2(const int8_t* adig, int64_t rows, int64_t rows_alloc, con
   int pass = 0;
   for (int64_t a0 = 0; a0 < n_sel; a0 += kMaxAtomsPerPass, ++pass) {
     int64_t a1 = a0 + kMaxAtomsPerPass < n_sel ? a0 + kMaxAtomsPerPass : n_sel;
-    project_tc2_kernel<<<2 * clusters, THREADS, SMEM_BYTES, s>>>(map_phase, map_traj, expo, P, (int)rows, (int)n_t, ldp,
+    project_tc2_kernel<<<2 * clusters, THREADS, SMEM_BYTES, s>>>(map_phase, map_traj, expo, P, (int)rows, (int)n_t, n_t_total, ldp,
                                                                  (int)a0, (int)a1, pass > 0, r_tiles, t_tiles);
     st = launch_status("project_tc2_kernel");
     if (st != PSA_OK) return st;

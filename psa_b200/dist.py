@@ -304,7 +304,7 @@ def _stream_fence(device, group=None) -> None:
     dist.all_reduce(torch.zeros(1, device=device), group=group)
 
 
-def sliced_ingest(calc, proj_groups, local_rows=None, group=None, marks=None) -> None:
+def sliced_ingest(calc, proj_groups, local_rows=None, group=None, marks=None, pipeline: Optional[bool] = None) -> None:
     """k-independent state from a trajectory whose FRAMES are spread over the ranks.
 
     Rank r uploads only frames ``shard_range(n_t, r, world)`` - 1/N of the bytes over its own PCIe link -
@@ -320,10 +320,20 @@ def sliced_ingest(calc, proj_groups, local_rows=None, group=None, marks=None) ->
     nothing but its range; otherwise the range is sliced out of ``calc.traj``.  On return every rank's device
     trajectory has the mean and the digit planes of ``proj_groups`` installed, exactly as after a one-GPU ingest.
     ``marks``: optional callable ``marks(name)`` recording a stage boundary on the stream (bench breakdown).
+
+    ``pipeline`` (default on; ``PSA_B200_PIPELINE_EXCHANGE=0`` turns it off): the peer stores run as a ring on a side
+    stream - step s sends this rank's rows to rank ``r + s`` while rank ``r - s``'s rows arrive - and the digit planes
+    are installed with that arrival schedule, so the first k-chunk's projection starts on the frames already present
+    (its own, then one peer's range per step) instead of waiting for the whole exchange (``engine.sed_on_device``).
     """
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     eng, dtraj = calc.engine, calc.device_trajectory
     mark = marks or (lambda name: None)
+    if pipeline is None:
+        pipeline = os.environ.get("PSA_B200_PIPELINE_EXCHANGE", "1") != "0"
+    main = torch.cuda.current_stream(eng.device) if eng.device.type == "cuda" else None
+    if main is not None and eng._comm_stream is not None:
+        main.wait_stream(eng._comm_stream)              # an exchange nobody consumed must not run into this one
     # skip only if EVERY rank already holds the state (a rank that computed something on its own must not
     # leave the others waiting in the chain)
     ready = torch.tensor([1 if dtraj.has_state(proj_groups, calc.use_displacements) else 0], device=eng.device)
@@ -348,12 +358,36 @@ def sliced_ingest(calc, proj_groups, local_rows=None, group=None, marks=None) ->
         pitch = int(eng_pitch(n_sel))
         key = dtraj._group_key(g, disp)[0]
         peers = _peer_planes(calc, (key, n_t, pitch), n_t, pitch, group)
+        if peers is not None and pipeline and world > 1 and all(a % 4 == 0 for a, _ in bounds):
+            _stream_fence(eng.device, group)            # nobody still projects from the planes of a previous ingest
+            own = ((ctypes.c_void_p * 1)(peers.dig_ptrs[rank]), (ctypes.c_void_p * 1)(peers.expo_ptrs[rank]))
+            mean_ptr = acc.data_ptr() if disp else None
+            w_ptr = None if dtraj.weight is None else dtraj.weight.data_ptr()
+            i_ptr = None if idx_dev is None else idx_dev.data_ptr()
+            eng._run("psa_digitize_rows_peers", 1, data_rows.data_ptr(), mean_ptr, w_ptr, i_ptr, t1 - t0, n_a, n_sel, pitch,
+                     ctypes.addressof(own[0]), ctypes.addressof(own[1]), 1, n_t, t0, 0, eng.stream())
+            arrivals = [(t0, t1, None)]
+            comm = eng.comm_stream
+            comm.wait_stream(main)                      # rows uploaded, mean final, fence passed
+            data_rows.record_stream(comm)
+            with torch.cuda.stream(comm):
+                for step in range(1, world):
+                    dst, src_rank = (rank + step) % world, (rank - step) % world
+                    one = ((ctypes.c_void_p * 1)(peers.dig_ptrs[dst]), (ctypes.c_void_p * 1)(peers.expo_ptrs[dst]))
+                    eng._run("psa_digitize_rows_peers", 1, data_rows.data_ptr(), mean_ptr, w_ptr, i_ptr, t1 - t0, n_a, n_sel,
+                             pitch, ctypes.addressof(one[0]), ctypes.addressof(one[1]), 1, n_t, t0, 1, eng.stream())
+                    _stream_fence(eng.device, group)    # every rank's step has landed: rank r - step's rows are here
+                    ev = torch.cuda.Event()
+                    ev.record(comm)
+                    arrivals.append((bounds[src_rank][0], bounds[src_rank][1], ev))
+            dtraj.install_group(idx, disp, peers.dig, peers.expo, arrivals=arrivals)
+            continue
         if peers is not None:
             _stream_fence(eng.device, group)            # nobody still projects from the planes of a previous ingest
             eng._run("psa_digitize_rows_peers", 1, data_rows.data_ptr(), acc.data_ptr() if disp else None,
                      None if dtraj.weight is None else dtraj.weight.data_ptr(),
                      None if idx_dev is None else idx_dev.data_ptr(), t1 - t0, n_a, n_sel, pitch,
-                     ctypes.addressof(peers.dig_ptrs), ctypes.addressof(peers.expo_ptrs), world, n_t, t0, eng.stream())
+                     ctypes.addressof(peers.dig_ptrs), ctypes.addressof(peers.expo_ptrs), world, n_t, t0, 0, eng.stream())
             _stream_fence(eng.device, group)            # every rank's rows have landed everywhere
             dig, expo = peers.dig, peers.expo
         else:

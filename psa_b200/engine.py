@@ -50,6 +50,41 @@ def effective_k_chunk(k_chunk_size: int, n_k: int) -> int:
     return -(-n_k // n_chunks)
 
 
+def plan_k_chunks(n_k: int, k_chunk_size: int, first_rows_hint: Optional[Tuple[int, int]] = None) -> List[Tuple[int, int]]:
+    """``[(k0, n_k_chunk), ...]``.  Normally equal chunks (:func:`effective_k_chunk`).  ``first_rows_hint =
+    (frames_per_range, n_clusters)``: the first chunk will be projected range by range while a multi-GPU exchange is
+    in flight, so it gets a whole number of 128-row tiles chosen such that ONE range launch fills whole waves of the
+    projection's CTA pairs (r tiles x ceil(frames / 256) x 3 polarisations ~ a multiple of n_clusters)."""
+    if n_k <= 0:
+        return []
+    kc = effective_k_chunk(k_chunk_size, n_k)
+    chunks: List[Tuple[int, int]] = []
+    k0 = 0
+    if first_rows_hint is not None and n_k >= 64 and kc >= 64:
+        frames, clusters = first_rows_hint
+        per_row_tile = -(-max(1, frames) // 256) * 3
+        best_r, best_eff = 1, 0.0
+        for r in range(1, min(16, min(n_k, kc) // 64) + 1):
+            waves = r * per_row_tile / clusters
+            eff = waves / -(-r * per_row_tile // clusters)
+            if eff >= best_eff - 0.02 or eff >= 0.95:           # prefer more tiles unless clearly less efficient
+                if eff >= 0.95 or eff > best_eff:
+                    best_r, best_eff = r, max(eff, best_eff if eff >= 0.95 else eff)
+        first = min(n_k, best_r * 64)
+        if n_k - first < 128 and n_k <= kc:                     # not worth a second, tiny launch
+            first = n_k
+        chunks.append((0, first))
+        k0 = first
+    rest = n_k - k0
+    if rest > 0:
+        kc_rest = effective_k_chunk(k_chunk_size, rest)
+        while k0 < n_k:
+            nk = min(kc_rest, n_k - k0)
+            chunks.append((k0, nk))
+            k0 += nk
+    return chunks
+
+
 @dataclass
 class HostTarget:
     """Where a streamed result goes: a page-locked host array of shape ``(n_rows, n_k_total[, 3])`` of which one call
@@ -82,6 +117,7 @@ class Engine:
         self._plans: Dict[int, torch.Tensor] = {}
         self._fft_ws: Optional[torch.Tensor] = None
         self._copy_stream: Optional[torch.cuda.Stream] = None
+        self._comm_stream: Optional[torch.cuda.Stream] = None
         self.launches = 0          # kernels launched through this engine (bench reports it)
         self.profile: Optional[Dict[str, List[Tuple[torch.cuda.Event, torch.cuda.Event, int]]]] = None
 
@@ -95,6 +131,18 @@ class Engine:
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         return self._copy_stream
+
+    @property
+    def comm_stream(self) -> "torch.cuda.Stream":
+        """Side stream of the multi-GPU exchange (peer stores + fences run under the first chunk's projection)."""
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        return self._comm_stream
+
+    @property
+    def n_clusters(self) -> int:
+        """CTA pairs the projection kernel runs (one per two SMs)."""
+        return max(1, torch.cuda.get_device_properties(self.device).multi_processor_count // 2)
 
     def empty(self, shape, dtype) -> torch.Tensor:
         return torch.empty(shape, dtype=dtype, device=self.device)
@@ -170,10 +218,17 @@ class Engine:
         return out
 
     def project(self, adig: torch.Tensor, rows: int, rows_alloc: int, bdig: torch.Tensor, expo: torch.Tensor,
-                n_t: int, n_sel: int, pitch: int, P: torch.Tensor, ldp: int, impl: Optional[int] = None) -> None:
-        self._run("psa_project", -(-n_sel // 32768), adig.data_ptr(), rows, rows_alloc, bdig.data_ptr(),
-                  expo.data_ptr(), n_t, n_sel, pitch, P.data_ptr(), ldp,
-                  self.project_impl if impl is None else impl, self.stream())
+                n_t: int, n_sel: int, pitch: int, P: torch.Tensor, ldp: int, impl: Optional[int] = None,
+                t_range: Optional[Tuple[int, int]] = None) -> None:
+        """``t_range = (t0, t1)`` projects those frames only (same bits as the full call, frame by frame)."""
+        impl = self.project_impl if impl is None else impl
+        if t_range is None:
+            self._run("psa_project", -(-n_sel // 32768), adig.data_ptr(), rows, rows_alloc, bdig.data_ptr(),
+                      expo.data_ptr(), n_t, n_sel, pitch, P.data_ptr(), ldp, impl, self.stream())
+        else:
+            t0, t1 = t_range
+            self._run("psa_project_rows", -(-n_sel // 32768), adig.data_ptr(), rows, rows_alloc, bdig.data_ptr(),
+                      expo.data_ptr(), n_t, t0, t1 - t0, n_sel, pitch, P.data_ptr(), ldp, impl, self.stream())
 
     def fft_plan(self, n_t: int) -> torch.Tensor:
         """Device-resident FFT plan for ``n_t`` frames (twiddles; chirp tables when n_t is not 2^s), cached."""
@@ -231,6 +286,7 @@ class DeviceTrajectory:
         self._dev: Dict[str, torch.Tensor] = {}
         self._mean: Optional[torch.Tensor] = None
         self._groups: Dict[Tuple, Tuple] = {}
+        self._arrivals: Dict[int, List[Tuple[int, int, Optional["torch.cuda.Event"]]]] = {}
         self._indices: Dict[Optional[str], torch.Tensor] = {}
         self._lock = threading.RLock()
         self.h2d_bytes = 0
@@ -325,6 +381,7 @@ class DeviceTrajectory:
         with self._lock:
             self._mean = None
             self._groups.clear()
+            self._arrivals.clear()
 
     @property
     def mean(self) -> torch.Tensor:
@@ -353,13 +410,23 @@ class DeviceTrajectory:
             self._mean = mean
 
     def install_group(self, idx: Optional[np.ndarray], use_displacements: bool, dig: torch.Tensor,
-                      expo: torch.Tensor) -> None:
-        """Adopt digit planes computed elsewhere for the atom selection ``idx``."""
+                      expo: torch.Tensor, arrivals=None) -> None:
+        """Adopt digit planes computed elsewhere for the atom selection ``idx``.  ``arrivals``: frame ranges
+        ``(t0, t1, event|None)`` in the order in which they become valid (a multi-GPU exchange still in flight on a
+        side stream): the first projection over these planes goes range by range, waiting for each event."""
         key, idx = self._group_key(idx, use_displacements)
         idx_dev = None if idx is None else self._index_tensor(key, idx)
         n_sel = self.n_a if idx is None else int(idx.size)
         with self._lock:
             self._groups[key] = (idx_dev, n_sel, int(dig.shape[-1]), dig, expo)
+            if arrivals:
+                self._arrivals[dig.data_ptr()] = list(arrivals)
+            else:
+                self._arrivals.pop(dig.data_ptr(), None)
+
+    def pop_arrivals(self, dig: torch.Tensor):
+        with self._lock:
+            return self._arrivals.pop(dig.data_ptr(), None)
 
     def prepare(self, groups: Sequence[Optional[np.ndarray]], use_displacements: bool) -> Tuple[torch.Tensor, List[Tuple]]:
         """Mean positions and the digit planes of every group (both cached).  Running the two passes on
@@ -417,7 +484,13 @@ def sed_on_device(traj: DeviceTrajectory, k_vecs: np.ndarray, groups: Sequence[O
     if n_k == 0:
         return out
     mean, entries = traj.prepare(groups, use_displacements)
-    kc = effective_k_chunk(k_chunk, n_k)
+    arrivals = [traj.pop_arrivals(e[3]) for e in entries]
+    hint = None
+    if any(arrivals):                       # a multi-GPU exchange is still in flight: first chunk goes range by range
+        longest = max(t1 - t0 for arr in arrivals if arr for t0, t1, _ in arr)
+        hint = (longest, eng.n_clusters)
+    chunks = plan_k_chunks(n_k, k_chunk, hint)
+    kc = max(nk for _, nk in chunks)
     window = traj.window
     rows_alloc = 2 * kc
     ldp = (n_t + 3) // 4 * 4
@@ -431,14 +504,21 @@ def sed_on_device(traj: DeviceTrajectory, k_vecs: np.ndarray, groups: Sequence[O
         chunk_bufs = [torch.empty((n_t, kc) + shape[2:], dtype=dtype, device=eng.device) for _ in range(2)]
         drained = [None, None]                                           # copy-stream events per buffer
         compute, copy = torch.cuda.current_stream(eng.device), eng.copy_stream
-    for ci, k0 in enumerate(range(0, n_k, kc)):
-        nk = min(kc, n_k - k0)
+    main = torch.cuda.current_stream(eng.device)
+    for ci, (k0, nk) in enumerate(chunks):
         for g, (idx_dev, n_sel, pitch, dig, expo) in enumerate(entries):
             adig = adig_bufs.get(pitch)
             if adig is None:
                 adig = adig_bufs[pitch] = eng.empty((4, rows_alloc, pitch), torch.int8)
             eng.phase_digits(kv_dev[k0:k0 + nk], mean, idx_dev, n_sel, pitch, rows_alloc, out=adig)
-            eng.project(adig, 2 * nk, rows_alloc, dig, expo, n_t, n_sel, pitch, P[g], ldp)
+            if ci == 0 and arrivals[g]:
+                for t0, t1, ev in arrivals[g]:            # frames in the order in which the peers' rows land
+                    if ev is not None:
+                        main.wait_event(ev)
+                    if t1 > t0:
+                        eng.project(adig, 2 * nk, rows_alloc, dig, expo, n_t, n_sel, pitch, P[g], ldp, t_range=(t0, t1))
+            else:
+                eng.project(adig, 2 * nk, rows_alloc, dig, expo, n_t, n_sel, pitch, P[g], ldp)
         if host_out is None:
             eng.fft_sed(P, len(entries), group_stride, nk, n_t, ldp, mode, out, n_k, k0, window)
             continue

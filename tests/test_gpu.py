@@ -194,6 +194,43 @@ def test_project_tensor_matches_integer_model(eng, rows, n_t, n_sel):
     np.testing.assert_array_equal(got, M.project(xa, xb, e))
 
 
+def test_projection_by_frame_ranges_is_bit_identical(eng):
+    """psa_project_rows: projecting a trajectory range by range (ragged ranges, not tile-aligned) gives the bits of the
+    one-shot call - what lets a multi-GPU run project the frames that have arrived while the rest is in flight."""
+    from psa_b200 import _lib
+    rows, n_t, n_sel = 200, 1000, 300
+    xa, xb, e = _proj_inputs(np.random.default_rng(77), rows, n_t, n_sel)
+    want = M.project(xa, xb, e)
+    pitch = -(-n_sel // 64) * 64
+    ad = np.zeros((4, rows, pitch), np.int8)
+    ad[:, :, :n_sel] = M.balanced_digits(xa)
+    bd = np.zeros((3, 4, n_t, pitch), np.int8)
+    for pol in range(3):
+        bd[pol, :, :, :n_sel] = M.balanced_digits(xb[pol])
+    ad_d, bd_d, e_d = dev(eng, ad), dev(eng, bd), dev(eng, e)
+    for impl in (_lib.PROJECT_TENSOR, _lib.PROJECT_SIMT):
+        P = torch.full((rows, 3, n_t), float("nan"), dtype=torch.float32, device=eng.device)
+        for t0, t1 in ((700, 1000), (0, 256), (256, 700)):                   # any order
+            eng.project(ad_d, rows, rows, bd_d, e_d, n_t, n_sel, pitch, P, n_t, impl=impl, t_range=(t0, t1))
+        np.testing.assert_array_equal(P.cpu().numpy(), want)
+
+
+def test_first_chunk_follows_an_arrival_schedule(gold_si):
+    """Digit planes installed with an arrival schedule (frame ranges + events, as the pipelined multi-GPU exchange does):
+    the first k-chunk is projected range by range, later chunks in one launch - same bits as the plain path."""
+    calc = _calc(gold_si)
+    kv = np.concatenate([gold_si["kpath_110_vecs"]] * 12)                   # 144 k-points: more than one chunk below
+    plain = calc.calculate(np.zeros(len(kv)), kv, k_chunk_size=500).sed
+    dtraj = calc.device_trajectory
+    idx_dev, n_sel, pitch, dig, expo = dtraj.group(None, False)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(calc.engine.device))
+    dtraj.install_group(None, False, dig, expo, arrivals=[(128, 256, None), (0, 64, ev), (64, 128, None)])
+    again = calc.calculate(np.zeros(len(kv)), kv, k_chunk_size=100).sed      # 2 chunks of 72: first one by ranges
+    np.testing.assert_array_equal(again, plain)
+    assert dtraj.pop_arrivals(dig) is None                                   # consumed
+
+
 def test_project_extreme_digits_no_overflow(eng):
     """Worst-case digits (every product at its maximum) over a full 32768-atom pass stay exact."""
     from psa_b200 import _lib

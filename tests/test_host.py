@@ -352,3 +352,19 @@ def test_cli_host_logic(tmp_path):
     with pytest.raises(ValueError):
         cli.resolve_basis(types, 5, {"atom_indices": [7], "atom_types": None})
     assert cli.main(["--trajectory", str(tmp_path / "none.lammpstrj"), "--output-dir", str(tmp_path / "o")]) == 1
+
+
+def test_k_chunk_planning():
+    """Equal chunks by default; with a frame-range hint (pipelined multi-GPU exchange) the first chunk is a whole number
+    of 128-row tiles that fills whole waves of CTA pairs per range launch."""
+    from psa_b200.engine import effective_k_chunk, plan_k_chunks
+    assert effective_k_chunk(500, 10000) == 1000 and effective_k_chunk(500, 200) == 200 and effective_k_chunk(7, 100) == 7
+    assert plan_k_chunks(10000, 500) == [(k, 1000) for k in range(0, 10000, 1000)]
+    assert plan_k_chunks(0, 500) == [] and plan_k_chunks(7, 3) == [(0, 3), (3, 3), (6, 1)]
+    first = plan_k_chunks(1250, 500, (2048, 74))
+    assert first == [(0, 576), (576, 674)]                 # 9 row tiles x 8 frame tiles x 3 = 216 tiles = 2.92 waves of 74
+    assert plan_k_chunks(200, 500, (8192, 74)) == [(0, 200)]
+    for n_k, hint in ((2500, (4096, 74)), (5000, (8192, 74)), (96, (1365, 74))):
+        chunks = plan_k_chunks(n_k, 500, hint)
+        assert chunks[0][0] == 0 and sum(nk for _, nk in chunks) == n_k
+        assert all(b[0] == a[0] + a[1] for a, b in zip(chunks, chunks[1:]))

@@ -228,3 +228,18 @@ def test_oracle_ised_and_chiral_equal_the_real_reference_on_random_inputs(seed):
     groups = G.resolve_ised_groups(types, n_a, spec.get("basis_atom_idx_ised"), spec.get("basis_atom_types_ised"))
     got = O.ised(pos, vel, types, dt, k_hat, mags, vecs, k_target, w_target, groups, rescale_factor=rescale, n_frames=5)
     np.testing.assert_array_equal(got["frames"], want)
+
+
+def test_numpy_complex64_fft_is_the_rounded_float64_transform():
+    """Why the CUDA FFT is carried in float64: the reference's `np.fft.fft(..., axis=0)` on complex64 data
+    (sed_calculator.py:83) returns, in the NumPy it runs on, exactly the float64 transform rounded once to complex64 -
+    every bin accurate to its own magnitude, weak bins next to a strong line included.  A float32-butterfly transform
+    cannot match that, whatever its twiddles."""
+    rng = np.random.default_rng(4)
+    for n in (250, 1000, 4096, 16384):
+        z = (rng.standard_normal((n, 5)) + 1j * rng.standard_normal((n, 5))).astype(np.complex64)
+        z[:, 0] += (30 * np.exp(2j * np.pi * 37 * np.arange(n) / n)).astype(np.complex64)       # a line 30x over the noise
+        got = np.fft.fft(z, axis=0)
+        assert got.dtype == np.complex64
+        want = np.fft.fft(z.astype(np.complex128), axis=0).astype(np.complex64)
+        np.testing.assert_array_equal(got, want)
