@@ -567,7 +567,9 @@ def main():
                         "step": "mean positions + digit planes + phase table + tcgen05 projection + FFT/assembly",
                         "collectives_in_value": None if world == 1 else
                         "N-1 send/recv hops + 1 broadcast of the (n_atoms, 3) running mean; digit planes exchanged by the "
-                        "digitise kernel's peer stores (NVLink) between two 1-element all-reduces; nothing during compute"},
+                        "digitise kernel's peer stores over NVLink as a ring of N-1 steps on a side stream, each fenced by a "
+                        "1-element all-reduce, running under the first k-chunk's projection (which follows the arrival "
+                        "order of the frame ranges); nothing else during compute"},
             "roofline": roof, "rooflines": rooflines, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "ised": ised,
             "int8_peak": int8_peak,
             "gpu_launches": int(launches), "gpu_launches_per_step": int(launches) // max(1, args.steps), "clocks": clocks,

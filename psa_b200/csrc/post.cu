@@ -158,12 +158,33 @@ __device__ __forceinline__ void ised_values(const IsedBatch& b, const IsedAtom& 
   }
 }
 
+// Store one frame of a warp: 32 atoms x 3 values = 384 contiguous bytes of the output.  kWide (n_a % 4 == 0): staged in
+// shared memory and written as 24 aligned 16-byte stores (three full 128-byte lines) instead of 96 4-byte pieces.
+template <bool kWide>
+__device__ __forceinline__ void ised_store_frame(float* __restrict__ row, float* __restrict__ st, int lane, int n_warp,
+                                                 bool live, const float (&val)[3]) {
+  if (kWide) {
+    st[lane * 3] = val[0];
+    st[lane * 3 + 1] = val[1];
+    st[lane * 3 + 2] = val[2];
+    __syncwarp();
+    if (lane * 4 < n_warp * 3)                                              // n_warp % 4 == 0 here: whole float4s only
+      __stcs(reinterpret_cast<float4*>(row) + lane, reinterpret_cast<const float4*>(st)[lane]);
+    // the caller alternates two staging buffers: this one is rewritten two frames from now, after another __syncwarp
+  } else if (live) {
+    row[lane * 3] = val[0];
+    row[lane * 3 + 1] = val[1];
+    row[lane * 3 + 2] = val[2];
+  }
+}
+
 // kWrite = false: max over (frame, atom of a group, pol) of |running sum after that group| per point -> wmax[p]
 //                 (the 'auto' rescale's max_wiggle_amp_all, sed_calculator.py:502-504), nothing is stored;
 // kWrite = true : out[p][f][a][pol] = mean + ((sum / div[p]) * mul[p]) in float32, the reference's order of operations
 //                 (sed_calculator.py:517-533); div = mul = 1 leaves the sum untouched bit for bit.
-// kWide: n_a % 4 == 0 - a warp's 32 atoms x 3 values of one frame (384 contiguous bytes of the output) are staged in
-// shared memory and leave as 24 aligned 16-byte stores (three full 128-byte lines per warp instead of 96 4-byte pieces).
+// A block whose atoms all belong to at most one group (the usual, disjoint-group case) runs a tight loop: per output
+// value two float64 FMAs, one conversion, the FMA-corrected division and the add - ~45 instructions per (atom, frame);
+// blocks with overlapping groups take the general running-sum loop.
 template <bool kWrite, bool kWide>
 __global__ void __launch_bounds__(128) ised_batch_kernel(IsedBatch b, const float* __restrict__ div,
                                                          const float* __restrict__ mul, float* __restrict__ out,
@@ -172,7 +193,6 @@ __global__ void __launch_bounds__(128) ised_batch_kernel(IsedBatch b, const floa
   __shared__ __align__(16) float stage[4][2][96];          // [warp][double buffer][32 atoms x 3]
   const int f_begin = blockIdx.z * kIsedFrameChunk, f_end = min(b.n_frames, f_begin + kIsedFrameChunk);
   ised_fill_phasors(phasor, f_begin, f_end, b.n_frames);
-  __syncthreads();
   const int p = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t a_warp = a - lane;                         // first atom of this warp
@@ -190,47 +210,55 @@ __global__ void __launch_bounds__(128) ised_batch_kernel(IsedBatch b, const floa
     at.m_end = __ldg(b.member_off + a + 1);
     if (at.m_end - at.m_begin == 1) ised_uv(b, p, __ldg(b.member_grp + at.m_begin), at.ca, at.sa, at.U, at.V);
   }
+  const bool overlapping = __syncthreads_or(live && at.m_end - at.m_begin > 1);   // also: the phasor table is complete
   const float dv = kWrite ? __ldg(div + p) : 1.f, ml = kWrite ? __ldg(mul + p) : 1.f;
   const bool rescale = dv != 1.f || ml != 1.f;                               // uniform over the block
   const FastDiv fdiv = make_fast_div(dv);
-  const bool single = at.m_end - at.m_begin == 1;                            // the usual case: disjoint groups
   float* o = kWrite ? out + (int64_t)p * b.n_frames * b.n_a * 3 : nullptr;
   const int n_warp = (int)min((int64_t)32, b.n_a - a_warp);                 // atoms of this warp that exist (<= 0: none)
-  for (int f = f_begin; f < f_end; ++f) {
-    const double2 cs = phasor[f - f_begin];
-    float w[3] = {0.f, 0.f, 0.f};
-    if (live) {
-      if (single) {
+  if (!overlapping) {
+    // tight loop; atoms in no group have U = V = 0 and come out as the mean
+    const float r = fdiv.r, d = fdiv.d;
+    const bool exact_fast = fdiv.usable;
+    for (int f = f_begin; f < f_end; ++f) {
+      const double2 cs = phasor[f - f_begin];
+      float val[3];
 #pragma unroll
-        for (int pol = 0; pol < 3; ++pol) {
-          w[pol] = (float)(cs.x * at.U[pol] + cs.y * at.V[pol]);
-          if (!kWrite) local_max = fmaxf(local_max, fabsf(w[pol]));
+      for (int pol = 0; pol < 3; ++pol) {
+        const float w = (float)(cs.x * at.U[pol] + cs.y * at.V[pol]);
+        if (!kWrite) {
+          local_max = fmaxf(local_max, fabsf(w));
+        } else {
+          float q = w;
+          if (rescale) {
+            if (exact_fast) {                                                // FMA-corrected division, see FastDiv
+              q = __fmul_rn(w, r);
+              q = __fmaf_rn(__fmaf_rn(-q, d, w), r, q);
+              q = __fmaf_rn(__fmaf_rn(-q, d, w), r, q);
+            } else {
+              q = __fdiv_rn(w, d);
+            }
+            q = __fmul_rn(q, ml);
+          }
+          val[pol] = __fadd_rn(at.mean[pol], q);
         }
-      } else {
-        ised_values(b, at, p, cs, w, local_max);
       }
+      if (kWrite)
+        ised_store_frame<kWide>(o + ((int64_t)f * b.n_a + a_warp) * 3, stage[warp][f & 1], lane, n_warp, live, val);
     }
-    if (!kWrite) continue;
-    float val[3];
+  } else {
+    for (int f = f_begin; f < f_end; ++f) {
+      const double2 cs = phasor[f - f_begin];
+      float w[3] = {0.f, 0.f, 0.f};
+      if (live) ised_values(b, at, p, cs, w, local_max);
+      if (!kWrite) continue;
+      float val[3];
 #pragma unroll
-    for (int pol = 0; pol < 3; ++pol) {
-      const float scaled = rescale ? __fmul_rn(fast_div(fdiv, w[pol]), ml) : w[pol];
-      val[pol] = __fadd_rn(at.mean[pol], scaled);
-    }
-    float* row = o + ((int64_t)f * b.n_a + a_warp) * 3;
-    if (kWide) {
-      float* st = stage[warp][f & 1];
-      st[lane * 3] = val[0];
-      st[lane * 3 + 1] = val[1];
-      st[lane * 3 + 2] = val[2];
-      __syncwarp();
-      if (lane * 4 < n_warp * 3)                                            // n_warp % 4 == 0 here: whole float4s only
-        __stcs(reinterpret_cast<float4*>(row) + lane, reinterpret_cast<const float4*>(st)[lane]);
-      // the other buffer is written next; this one again two frames from now, after the next __syncwarp
-    } else if (live) {
-      row[lane * 3] = val[0];
-      row[lane * 3 + 1] = val[1];
-      row[lane * 3 + 2] = val[2];
+      for (int pol = 0; pol < 3; ++pol) {
+        const float scaled = rescale ? __fmul_rn(fast_div(fdiv, w[pol]), ml) : w[pol];
+        val[pol] = __fadd_rn(at.mean[pol], scaled);
+      }
+      ised_store_frame<kWide>(o + ((int64_t)f * b.n_a + a_warp) * 3, stage[warp][f & 1], lane, n_warp, live, val);
     }
   }
   if (!kWrite) {
