@@ -11,9 +11,10 @@ the largest configuration BASELINE.json names for 1/2/4/8 GPUs.  Units are (k-po
 * ``value``: inputs already resident in HBM.  N = 1: the raw float32 trajectory is on the device, the result stays
   there.  N > 1 (torchrun, one rank per GPU): STRONG scaling of the same job - the frames are resident in HBM spread
   over the ranks (rank r holds frames ``shard_range(n_t, r, N)``), every step runs the sliced ingest (ordered float32
-  mean chain rank to rank, every rank's digitise kernel storing its rows into all ranks' digit planes through
-  NVLink, two one-element all-reduces as stream fences) and then each rank projects + transforms its 1/N of the
-  k-points.  The collectives inside the timed region are exactly those.
+  mean chain rank to rank; the digitise kernel storing each rank's rows into all ranks' digit planes through NVLink,
+  as a ring of N-1 steps fenced by one-element all-reduces on a side stream, under the first k-chunk's projection)
+  and each rank projects + transforms its 1/N of the k-points.  The collectives inside the timed region are exactly
+  those.
 * ``e2e``: the public call on HOST (pinned) arrays - ``SEDCalculator.calculate`` (N = 1) or
   ``psa_b200.dist.calculate_sharded(ingest="sliced")`` (N > 1): H2D of positions + velocities (1/N per rank over its
   own PCIe link), the same kernels and exchange, D2H of every rank's spectra into one shared pinned host array.
