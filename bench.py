@@ -10,11 +10,13 @@ the largest configuration BASELINE.json names for 1/2/4/8 GPUs.  Units are (k-po
 
 * ``value``: inputs already resident in HBM.  N = 1: the raw float32 trajectory is on the device, the result stays
   there.  N > 1 (torchrun, one rank per GPU): STRONG scaling of the same job - the frames are resident in HBM spread
-  over the ranks (rank r holds frames ``shard_range(n_t, r, N)``), every step runs the sliced ingest (ordered float32
-  mean chain rank to rank; the digitise kernel storing each rank's rows into all ranks' digit planes through NVLink,
-  as a ring of N-1 steps fenced by one-element all-reduces on a side stream, under the first k-chunk's projection)
-  and each rank projects + transforms its 1/N of the k-points.  The collectives inside the timed region are exactly
-  those.
+  over the ranks (rank r holds frames ``shard_range(n_t, r, N)``).  Every step: ordered float32 mean chain rank to
+  rank; each rank digitises ITS frames and projects them for ALL k-points, the projection kernel's epilogue storing
+  every tile through NVLink into the buffer of the rank that owns those k-points (the frames->k all-to-all fused into
+  the tensor-core kernel, ``dist.frame_sharded_sed``); one one-element all-reduce per k-chunk as the fence; each
+  rank then transforms its 1/N of the k-points.  The collectives inside the timed region are exactly those.
+  (``PSA_B200_SHARD=k``: the previous scheme - digit planes all-gathered by the digitise kernel's peer stores,
+  k-sharded projection.)
 * ``e2e``: the public call on HOST (pinned) arrays - ``SEDCalculator.calculate`` (N = 1) or
   ``psa_b200.dist.calculate_sharded(ingest="sliced")`` (N > 1): H2D of positions + velocities (1/N per rank over its
   own PCIe link), the same kernels and exchange, D2H of every rank's spectra into one shared pinned host array.
@@ -220,6 +222,30 @@ def run_reference(args, cfg):
     emit(line)
 
 
+def timeline_stages(marks, d2h_bytes):
+    """Stage breakdown of one single-GPU public call from ``Engine.timeline`` marks (ms on the device's clock)."""
+    def at(label, which):
+        hits = [t for name, t in marks if name == label]
+        return None if not hits else (hits[0] if which == "first" else hits[-1])
+    out = {}
+    ingest, last_range = at("ingest", "first"), at("range_on_device", "last")
+    prefix, last_fft, first_fft = at("prefix_projected", "last"), at("chunk_transformed", "last"), at("chunk_transformed", "first")
+    last_host = at("chunk_on_host", "last")
+    if ingest is not None:
+        out["positions_upload_mean" + ("" if last_range is not None else "_velocities_digitize")] = ingest
+    if last_range is not None:
+        out["velocity_ranges_upload_digitize"] = last_range - ingest
+        if prefix is not None:
+            out["streamed_chunks_projection_tail"] = prefix - last_range
+    if last_fft is not None:
+        out["compute_rest"] = last_fft - (prefix if prefix is not None else ingest)
+    if last_host is not None and last_fft is not None:
+        out["drain_tail"] = last_host - last_fft
+        if first_fft is not None and last_host > first_fft:
+            out["d2h_GBps_while_draining"] = d2h_bytes / (last_host - first_fft) / 1e6
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ roofline
 def peaks():
     path = ROOT / "MEASURED_PEAKS.json"
@@ -383,8 +409,11 @@ def main():
         outs = []
         for (mags, vecs, kw, pair), (k0, k1) in zip(jobs, slices):
             if world > 1:
-                pdist.sliced_ingest(calc, proj_groups_of(kw)[1], rows_dev)
-            out, _, _ = calc._calculate_device(vecs[k0:k1], None, kw["basis_atom_types"], kw["summation_mode"])
+                cplx_, groups_ = proj_groups_of(kw)
+                out = pdist.sharded_sed_on_device(calc, np.ascontiguousarray(vecs, np.float32).reshape(-1, 3), groups_,
+                                                  cplx_, rows_dev)
+            else:
+                out, _, _ = calc._calculate_device(vecs[k0:k1], None, kw["basis_atom_types"], kw["summation_mode"])
             if pair is not None:
                 outs.append(calc._chiral_phase_of_result(out, pair))
             outs.append(out)
@@ -402,13 +431,17 @@ def main():
     t0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    marks = []
     for _ in range(args.steps):
         step_resident()
+        marks.append(torch.cuda.Event(enable_timing=True))
+        marks[-1].record()
     ev1.record()
     barrier()
     t1 = time.time()
     clocks = sampler.stop(t0, t1)
     ms_per_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    per_step = [a.elapsed_time(b) for a, b in zip([ev0] + marks[:-1], marks)]     # this rank; shows the power-cap drift
     launches = eng.launches - launches0                         # this rank's kernels inside the timed region
 
     jobs_full = [(j, (0, len(j[1]))) for j in jobs]
@@ -426,14 +459,16 @@ def main():
     cplx, proj_groups = proj_groups_of(jobs[0][2])
     n_sel_sum = sum(int(p.size) for p in proj_groups)
     rows_local = (f1 - f0) if world > 1 else n_t
+    frames_path = world > 1 and pdist.last_path == "frames"
     work = {
         "psa_project": FLOP_PER_UNIT * units_local,                                           # flops
         "psa_mean_positions": 12.0 * n_t * n_a,                                               # bytes
         "psa_mean_accumulate": 12.0 * rows_local * n_a,
-        "psa_digitize": 24.0 * n_t * n_sel_sum,
+        "psa_digitize": 24.0 * rows_local * n_sel_sum,
         "psa_digitize_rows": 24.0 * rows_local * n_sel_sum,
         "psa_digitize_rows_peers": (12.0 + 12.0 * world) * rows_local * n_sel_sum,           # read once, stored on N ranks
-        "psa_phase_digits": 8.0 * units_local / max(n_t, 1),
+        # frame-sharded: every rank builds the phase table of ALL k-points (for its own frames)
+        "psa_phase_digits": 8.0 * (units_total if frames_path else units_local) / max(n_t, 1),
         "psa_fft_sed": (48.0 if cplx else 24.0 * len(proj_groups) + 4.0) * n_k_local * n_t,
         "psa_chiral_phase": 20.0 * n_k_local * n_t,
     }
@@ -486,13 +521,25 @@ def main():
         if world > 1:                                           # one extra, untimed call for the stage breakdown
             step_e2e(timings=stage_ms)
             barrier()
+        else:
+            eng.timeline = []
+            step_e2e()
+            marks = eng.timeline_ms()
+            eng.timeline = None
+            stage_ms.update(timeline_stages(marks, d2h[0]))
         e2e = {"value": units_total / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                "steps": n_e2e, "h2d_bytes_per_step": int(2 * n_t * n_a * 12), "d2h_bytes_per_step": int(d2h[0]),
                "stage_ms_rank0": {k: round(v, 3) for k, v in stage_ms.items()} or None,
-               "path": "SEDCalculator.calculate on pinned host arrays" if world == 1 else
+               "path": "SEDCalculator.calculate on pinned host arrays (velocity ranges copied + digitised on a side stream "
+                       "while the leading k-chunks are projected range by range; k-chunks leave for the pinned result "
+                       "while the next one is computed)" if world == 1 else
                        "psa_b200.dist.calculate_sharded(ingest='sliced'): every rank uploads 1/N of the frames over its own "
-                       "PCIe link, float32 mean chain, digit planes stored into every rank through NVLink by the digitise "
-                       "kernel, k-sharded compute, every rank's spectra copied into one shared pinned host array"}
+                       "PCIe link, float32 mean chain, " +
+                       ("each rank projects its frames for all k-points with the tiles stored into the owner ranks through "
+                        "NVLink by the projection kernel, owners transform their k-slice, "
+                        if pdist.last_path == "frames" else
+                        "digit planes stored into every rank through NVLink by the digitise kernel, k-sharded compute, ") +
+                       "every rank's spectra copied into one shared pinned host array"}
 
         # ---------------- multi-GPU parity: a few k columns of the sharded result against a single-GPU compute, bitwise
         if world > 1:
@@ -566,11 +613,19 @@ def main():
                         "l2_policy": "inputs larger than L2 (trajectory %.0f MB per array%s)"
                                      % (n_t * n_a * 12 / 1e6, "" if world == 1 else f", 1/{world} per rank"),
                         "step": "mean positions + digit planes + phase table + tcgen05 projection + FFT/assembly",
+                        "step_ms_first_median_last": [round(per_step[0], 3), round(float(np.median(per_step)), 3),
+                                                      round(per_step[-1], 3)],
+                        "multi_gpu_path": None if world == 1 else pdist.last_path,
                         "collectives_in_value": None if world == 1 else
-                        "N-1 send/recv hops + 1 broadcast of the (n_atoms, 3) running mean; digit planes exchanged by the "
-                        "digitise kernel's peer stores over NVLink as a ring of N-1 steps on a side stream, each fenced by a "
-                        "1-element all-reduce, running under the first k-chunk's projection (which follows the arrival "
-                        "order of the frame ranges); nothing else during compute"},
+                        ("N-1 send/recv hops + 1 broadcast of the (n_atoms, 3) running mean; every rank projects its own "
+                         "frames for all k-points and the projection kernel stores each tile into the owner rank's buffer "
+                         "through NVLink (frames->k all-to-all fused into the tcgen05 kernel); 1-element all-reduces as "
+                         "fences (one at the start, one per k-chunk on a side stream); no digit plane leaves its GPU"
+                         if pdist.last_path == "frames" else
+                         "N-1 send/recv hops + 1 broadcast of the (n_atoms, 3) running mean; digit planes exchanged by the "
+                         "digitise kernel's peer stores over NVLink as a ring of N-1 steps on a side stream, each fenced by a "
+                         "1-element all-reduce, running under the first k-chunk's projection (which follows the arrival "
+                         "order of the frame ranges); nothing else during compute")},
             "roofline": roof, "rooflines": rooflines, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "ised": ised,
             "int8_peak": int8_peak,
             "gpu_launches": int(launches), "gpu_launches_per_step": int(launches) // max(1, args.steps), "clocks": clocks,

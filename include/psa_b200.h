@@ -109,7 +109,11 @@ int psa_phase_digits(const float* kvecs, int64_t n_k, const float* mean, const i
 /* Projection  P[row][pol][t] = sum_atoms phase[row][atom] * data[t][atom][pol]  (exact integer
  * contraction of the digit planes, one float32 rounding at the end).  Replaces the einsum/cgemm loop
  * (reference: sed_calculator.py:80-81).
- *   P [rows][3][ldp] float32, ldp >= n_t and ldp % 4 == 0;  impl = PSA_PROJECT_* */
+ *   P [rows][3][ldp] float32, ldp >= n_t and ldp % 4 == 0;  impl = PSA_PROJECT_*
+ * P may live on a PEER GPU (mapped with psa_ipc_open): a frame-sharded multi-GPU run projects its own frames for the
+ * k-points another rank owns and the epilogue's 128-byte row stores go straight into that rank's buffer through
+ * NVLink, at the column offset of this rank's frames (pass P + first_frame, ldp = the owner's row pitch) - the
+ * frames-to-k transpose (an all-to-all) is fused into the projection.  The kernel runs on adig's device. */
 int psa_project(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig,
                 const int32_t* expo, int64_t n_t, int64_t n_sel, int64_t pitch, float* P, int64_t ldp,
                 int impl, void* stream);

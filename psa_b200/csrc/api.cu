@@ -194,7 +194,7 @@ int psa_project_rows(const int8_t* adig, int64_t rows, int64_t rows_alloc, const
   PSA_REQUIRE(((uintptr_t)adig % 16) == 0 && ((uintptr_t)bdig % 16) == 0 && ((uintptr_t)P % 16) == 0,
               "psa_project: buffers must be 16-byte aligned");
   if (n_t_rows == 0) return PSA_OK;
-  DeviceGuard guard(P);
+  DeviceGuard guard(adig);       // P may be a peer GPU's buffer (frame-sharded multi-GPU): the phase digits are always local
   const int8_t* b0 = bdig + t0 * pitch;
   const int32_t* e0 = expo + t0;
   float* p0 = P + t0;

@@ -360,7 +360,7 @@ int launch_project_tc2(const int8_t* adig, int64_t rows, int64_t rows_alloc, con
                        int64_t ldp, cudaStream_t s) {
   using namespace tc2;
   if (rows == 0 || n_t == 0) return PSA_OK;
-  DeviceGuard guard(P);
+  DeviceGuard guard(adig);
   PSA_REQUIRE(n_sel > 0, "psa_project: empty atom selection");
   PSA_REQUIRE(rows < (1 << 30) && n_t < (1 << 30) && n_sel < (1 << 30), "psa_project: extent too large");
   CUtensorMap map_phase, map_traj;

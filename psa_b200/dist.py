@@ -216,6 +216,38 @@ def eng_pitch(n_sel: int) -> int:
     return int(_lib.load().psa_pitch(n_sel))
 
 
+# ---------------------------------------------------------------------------------------------- CUDA IPC mappings
+# A peer allocation can be mapped once per process at a time, and the caching allocator may carve several of our
+# buffers out of one allocation: mappings are shared process-wide and reference counted.
+_IPC_MAPPED: Dict[bytes, List[int]] = {}          # handle -> [base address, references]
+
+
+def _ipc_map(handle: bytes) -> int:
+    from . import _lib
+    hit = _IPC_MAPPED.get(handle)
+    if hit is None:
+        out = ctypes.c_void_p(0)
+        buf = ctypes.create_string_buffer(handle, 64)
+        _lib.call("psa_ipc_open", ctypes.addressof(buf), ctypes.addressof(out))
+        hit = _IPC_MAPPED[handle] = [int(out.value), 0]
+    hit[1] += 1
+    return hit[0]
+
+
+def _ipc_unmap(handle: bytes) -> None:
+    from . import _lib
+    hit = _IPC_MAPPED.get(handle)
+    if hit is None:
+        return
+    hit[1] -= 1
+    if hit[1] <= 0:
+        del _IPC_MAPPED[handle]
+        try:
+            _lib.call("psa_ipc_close", hit[0])
+        except Exception:
+            pass
+
+
 # ---------------------------------------------------------------------------------------------- peer-mapped planes
 class PeerPlanes:
     """Digit planes + exponents of one atom selection on this rank, plus the same buffers of every peer rank mapped
@@ -249,21 +281,14 @@ class PeerPlanes:
                     continue
                 base = self._opened.get(handle)
                 if base is None:
-                    out = ctypes.c_void_p(0)
-                    buf = ctypes.create_string_buffer(handle, 64)
-                    _lib.call("psa_ipc_open", ctypes.addressof(buf), ctypes.addressof(out))
-                    base = self._opened[handle] = int(out.value)
+                    base = self._opened[handle] = _ipc_map(handle)
                 ptrs[which][r] = base + off
         self.dig_ptrs = (ctypes.c_void_p * self.world)(*ptrs[0])
         self.expo_ptrs = (ctypes.c_void_p * self.world)(*ptrs[1])
 
     def close(self) -> None:
-        from . import _lib
-        for base in self._opened.values():
-            try:
-                _lib.call("psa_ipc_close", base)
-            except Exception:
-                pass
+        for handle in self._opened:
+            _ipc_unmap(handle)
         self._opened = {}
 
     def __del__(self):
@@ -304,6 +329,25 @@ def _stream_fence(device, group=None) -> None:
     dist.all_reduce(torch.zeros(1, device=device), group=group)
 
 
+def _upload_and_mean(calc, local_rows, group, mark):
+    """This rank's frame range on the device + the float32 mean positions of the WHOLE trajectory on every rank (the
+    ordered chain of running sums).  Returns ``(rows to project, mean, frame bounds of every rank)``."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    eng, dtraj = calc.engine, calc.device_trajectory
+    n_t, n_a = dtraj.n_t, dtraj.n_a
+    bounds = [shard_range(n_t, r, world) for r in range(world)]
+    t0, t1 = bounds[rank]
+    disp = calc.use_displacements
+    pos_rows = dtraj.upload_rows("pos", t0, t1, None if local_rows is None else local_rows[0])
+    data_rows = pos_rows if disp else dtraj.upload_rows("vel", t0, t1, None if local_rows is None else local_rows[1])
+    mark("upload")
+    acc = chain_running_sum(torch.zeros((n_a, 3), dtype=torch.float32, device=eng.device),
+                            lambda a, last: eng.mean_accumulate(pos_rows, a, n_t if last else 0), group)
+    dtraj.install_mean(acc)
+    mark("mean_chain")
+    return data_rows, acc, bounds
+
+
 def sliced_ingest(calc, proj_groups, local_rows=None, group=None, marks=None, pipeline: Optional[bool] = None) -> None:
     """k-independent state from a trajectory whose FRAMES are spread over the ranks.
 
@@ -341,17 +385,9 @@ def sliced_ingest(calc, proj_groups, local_rows=None, group=None, marks=None, pi
     if int(ready.item()) == 1:
         return
     n_t, n_a = dtraj.n_t, dtraj.n_a
-    bounds = [shard_range(n_t, r, world) for r in range(world)]
-    t0, t1 = bounds[rank]
     disp = calc.use_displacements
-    pos_rows = dtraj.upload_rows("pos", t0, t1, None if local_rows is None else local_rows[0])
-    data_rows = pos_rows if disp else dtraj.upload_rows("vel", t0, t1, None if local_rows is None else local_rows[1])
-    mark("upload")
-
-    acc = chain_running_sum(torch.zeros((n_a, 3), dtype=torch.float32, device=eng.device),
-                            lambda a, last: eng.mean_accumulate(pos_rows, a, n_t if last else 0), group)
-    dtraj.install_mean(acc)
-    mark("mean_chain")
+    data_rows, acc, bounds = _upload_and_mean(calc, local_rows, group, mark)
+    t0, t1 = bounds[rank]
 
     for g in proj_groups:
         idx, idx_dev, n_sel = dtraj.selection(g, disp)
@@ -397,6 +433,275 @@ def sliced_ingest(calc, proj_groups, local_rows=None, group=None, marks=None, pi
             exchange_row_blocks(list(dig.view(12, n_t, pitch).unbind(0)) + list(expo.unbind(0)), bounds, group)
         dtraj.install_group(idx, disp, dig, expo)
     mark("digitize_exchange")
+
+
+# ---------------------------------------------------------------------------------------------- frame-sharded path
+FRAME_K_CAP = 2048        # k-points per projection launch of the frame-sharded path (one owner's chunk)
+
+
+class PeerBuffers:
+    """``count`` equal device buffers of this rank plus the same buffers of every peer rank mapped into this process
+    through CUDA IPC (``ptrs[i][rank]`` = device address of buffer i on that rank).  Collective; the buffers must
+    outlive the peers' mappings, so they are owned here and reused by every call that fits into them."""
+
+    def __init__(self, eng, nbytes: int, count: int, group=None):
+        from . import _lib
+        self.world, self.rank, self.nbytes = dist.get_world_size(group), dist.get_rank(group), int(nbytes)
+        self.local = [eng.empty((self.nbytes,), torch.uint8) for _ in range(count)]
+        mine, failed = [], None
+        try:
+            for t in self.local:
+                handle = (ctypes.c_char * 64)()
+                off = ctypes.c_int64(0)
+                _lib.call("psa_ipc_export", t.data_ptr(), ctypes.addressof(handle), ctypes.addressof(off))
+                mine.append((bytes(handle), int(off.value)))
+        except (RuntimeError, ValueError, NotImplementedError) as exc:
+            mine, failed = None, exc
+        everyone: List = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)           # every rank reaches this, failed or not
+        self._opened: Dict[bytes, int] = {}
+        if any(e is None for e in everyone):
+            raise RuntimeError(f"CUDA IPC export failed on a rank ({failed})")
+        self.ptrs = [[0] * self.world for _ in range(count)]
+        for r, handles in enumerate(everyone):
+            for i, (handle, off) in enumerate(handles):
+                if r == self.rank:
+                    self.ptrs[i][r] = self.local[i].data_ptr()
+                    continue
+                base = self._opened.get(handle)
+                if base is None:
+                    base = self._opened[handle] = _ipc_map(handle)
+                self.ptrs[i][r] = base + off
+
+    def close(self) -> None:
+        for handle in self._opened:
+            _ipc_unmap(handle)
+        self._opened = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def frame_shard_plan(n_k: int, world: int, k_cap: int = FRAME_K_CAP):
+    """Who owns which k-points in a frame-sharded run and how the owners' slices are cut into projection chunks.
+    Returns ``(slices, n_chunks, chunk)``: ``slices[q]`` = rank q's contiguous k-range (the layout of the k-sharded
+    path and of the shared result), ``chunk(q, j)`` = the j-th of ``n_chunks`` balanced pieces of it (possibly empty).
+    Every rank evaluates the same plan."""
+    slices = [shard_range(n_k, q, world) for q in range(world)]
+    longest = max(b - a for a, b in slices)
+    n_chunks = max(1, -(-longest // max(1, int(k_cap))))
+
+    def chunk(q: int, j: int) -> Tuple[int, int]:
+        a, b = slices[q]
+        c0, c1 = shard_range(b - a, j, n_chunks)
+        return a + c0, a + c1
+
+    return slices, n_chunks, chunk
+
+
+def _all_agree(ok: bool, device, group=None) -> bool:
+    flag = torch.tensor([1 if ok else 0], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return int(flag.item()) == 1
+
+
+def _frame_buffers(calc, nbytes: int, group=None) -> Optional[PeerBuffers]:
+    """Three peer-mapped projection buffers of at least ``nbytes`` (cached on the calculator, grown collectively), or
+    ``None`` when peer mapping is not possible on every rank."""
+    eng = calc.engine
+    world = dist.get_world_size(group)
+    if os.environ.get("PSA_B200_PEER_STORES", "1") == "0" or world > 8 or dist.get_backend(group) != "nccl":
+        return None
+    have = calc.__dict__.get("_frame_buffers")
+    if have is False:
+        return None
+    if have is not None and have.nbytes >= nbytes:
+        return have
+    if have is not None:                     # grow: every rank unmaps its peers before anybody frees
+        have.close()
+        torch.cuda.synchronize(eng.device)
+        dist.barrier(group=group)
+        calc.__dict__["_frame_buffers"] = have = None
+    try:
+        have = PeerBuffers(eng, nbytes, 3, group)
+    except (RuntimeError, ValueError, NotImplementedError):
+        have = None
+    if not _all_agree(have is not None, eng.device, group):
+        have = None
+    calc.__dict__["_frame_buffers"] = have if have is not None else False
+    return have
+
+
+def frame_sharded_sed(calc, k_vecs: np.ndarray, proj_groups, complex_out: bool, local_rows=None, group=None,
+                      host_out=None, marks=None, k_chunk_size: int = 500) -> Tuple[bool, Optional[torch.Tensor]]:
+    """The SED of ``k_vecs`` with the FRAMES of the trajectory spread over the ranks - no digit plane ever leaves the
+    GPU that produced it.
+
+    Rank r uploads and digitises frames ``shard_range(n_t, r, N)`` only (the float32 mean still comes from the ordered
+    chain of running sums).  Every rank then projects ITS frames for ALL k-points, owner by owner: the k-points are
+    owned as in the k-sharded layout (``shard_range(n_k, q, N)``), and the projection kernel's epilogue stores each
+    tile straight into the owner's projection buffer through NVLink (CUDA-IPC mapped, column offset = this rank's first
+    frame) - the frames->k transpose, an all-to-all of 24 bytes per (k, frame), is fused into the tensor-core kernel;
+    rank r works on owner ``r + s`` at step s, so every NVLink port carries one stream at a time.  One stream-ordered
+    one-element all-reduce per chunk (on a side stream, under the next chunk's projection; three rotating buffers)
+    tells the owners that all frames of a chunk have landed; they run the time FFT + assembly on their k-slice.
+
+    Compared with all-gathering the digit planes (k-sharded path) this moves ``2 n_k / (N n_atoms)`` of the bytes
+    (C4 on 8 GPUs: 0.43 GB instead of 2.4 GB per rank, C5: 0.09 GB instead of 22 GB) and needs 1/N of the plane memory.
+    Bit-identical to one GPU: every (k, frame) of the projection is an independent exact sum.
+
+    Returns ``(True, result)`` - ``result`` = this rank's k-slice ``(n_t, n_k_local[, 3])`` on the device, or ``None``
+    when ``host_out`` (a :class:`engine.HostTarget` whose ``k_offset`` is this rank's first k) received it - or
+    ``(False, None)`` when this path cannot run (no peer mapping, frame ranges not multiples of 4, a rank without
+    frames): the caller falls back to the k-sharded path.  The decision is collective."""
+    from . import _lib
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    eng, dtraj = calc.engine, calc.device_trajectory
+    mark = marks or (lambda name: None)
+    n_t, n_a, n_k = dtraj.n_t, dtraj.n_a, int(k_vecs.shape[0])
+    bounds = [shard_range(n_t, r, world) for r in range(world)]
+    if any(a % 4 or b <= a for a, b in bounds) or n_k == 0:
+        return False, None
+    k_cap = FRAME_K_CAP if k_chunk_size >= 500 else max(1, int(k_chunk_size))
+    slices, n_chunks, chunk = frame_shard_plan(n_k, world, k_cap)
+    kc = max(chunk(q, j)[1] - chunk(q, j)[0] for q in range(world) for j in range(n_chunks))
+    n_groups = len(proj_groups)
+    ldp = (n_t + 3) // 4 * 4
+    p_rows = 2 * kc
+    group_stride = p_rows * 3 * ldp
+    bufs = _frame_buffers(calc, n_groups * group_stride * 4, group)
+    if bufs is None:
+        return False, None
+    f0, f1 = bounds[rank]
+    n_loc = f1 - f0
+    disp = calc.use_displacements
+    main = torch.cuda.current_stream(eng.device)
+    comm = eng.comm_stream
+    main.wait_stream(comm)
+    _stream_fence(eng.device, group)          # no owner still transforms out of the buffers this call will overwrite
+
+    # ---- k-independent state: mean positions (all ranks) + digit planes of this rank's frames (cached)
+    local = dtraj._frame_local
+    keys = [dtraj._group_key(g, disp)[0] for g in proj_groups]
+    cached = dtraj._mean is not None and local.get("bounds") == (f0, f1) and all(k in local.get("groups", {}) for k in keys)
+    if not _all_agree(cached, eng.device, group):
+        data_rows, mean, _ = _upload_and_mean(calc, local_rows, group, mark)
+        local.clear()
+        local.update(bounds=(f0, f1), groups={})
+        for key, g in zip(keys, proj_groups):
+            _, idx_dev, n_sel = dtraj.selection(g, disp)
+            dig, expo, pitch = eng.digitize(data_rows, mean if disp else None, idx_dev, n_sel, dtraj.weight)
+            local["groups"][key] = (idx_dev, n_sel, pitch, dig, expo)
+        mark("digitize_exchange")
+    mean = dtraj.mean
+    entries = [local["groups"][k] for k in keys]
+
+    # ---- projection of the local frames, owner by owner, stored into the owners' buffers
+    k0_own, k1_own = slices[rank]
+    n_k_own = k1_own - k0_own
+    shape = (n_t, n_k_own, 3) if complex_out else (n_t, n_k_own)
+    dtype = torch.complex64 if complex_out else torch.float32
+    mode = _lib.MODE_COHERENT if complex_out else _lib.MODE_INCOHERENT
+    window = dtraj.window
+    out = None
+    if host_out is None:
+        out = torch.empty(shape, dtype=dtype, device=eng.device)
+    else:
+        elem = 24 if complex_out else 4
+        n_rows = max(0, min(int(host_out.n_rows), n_t))
+        chunk_bufs = [torch.empty((n_t, kc) + shape[2:], dtype=dtype, device=eng.device) for _ in range(2)]
+        drained = [None, None]
+        copy = eng.copy_stream
+    kv_dev = eng.upload_small(np.ascontiguousarray(k_vecs, np.float32))
+    adig_bufs: Dict[int, torch.Tensor] = {}
+    p_local = [b.view(torch.float32) for b in bufs.local]
+    fences: List[Optional[torch.cuda.Event]] = [None] * n_chunks
+    n_done = 0
+
+    def transform(j: int) -> None:
+        """FFT + assembly of this rank's chunk j (all frames have landed: fence j has passed)."""
+        nonlocal n_done
+        main.wait_event(fences[j])
+        ka, kb = chunk(rank, j)
+        nk = kb - ka
+        if nk == 0:
+            return
+        P = p_local[j % 3]
+        if host_out is None:
+            eng.fft_sed(P, n_groups, group_stride, nk, n_t, ldp, mode, out, n_k_own, ka - k0_own, window)
+            return
+        b = n_done & 1
+        n_done += 1
+        if drained[b] is not None:
+            main.wait_event(drained[b])
+        eng.fft_sed(P, n_groups, group_stride, nk, n_t, ldp, mode, chunk_bufs[b], kc, 0, window)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        copy.wait_event(ready)
+        _lib.call("psa_copy_rows", host_out.ptr + (host_out.k_offset + ka - k0_own) * elem, host_out.n_k_total * elem,
+                  chunk_bufs[b].data_ptr(), kc * elem, nk * elem, n_rows, copy.cuda_stream)
+        drained[b] = torch.cuda.Event()
+        drained[b].record(copy)
+
+    for j in range(n_chunks):
+        for s in range(world):
+            q = (rank + s) % world
+            ka, kb = chunk(q, j)
+            nk = kb - ka
+            if nk == 0:
+                continue
+            for g, (idx_dev, n_sel, pitch, dig, expo) in enumerate(entries):
+                adig = adig_bufs.get(pitch)
+                if adig is None:
+                    adig = adig_bufs[pitch] = eng.empty((4, p_rows, pitch), torch.int8)
+                eng.phase_digits(kv_dev[ka:kb], mean, idx_dev, n_sel, pitch, p_rows, out=adig)
+                dst = bufs.ptrs[j % 3][q] + 4 * (g * group_stride + f0)
+                eng._run("psa_project", -(-n_sel // 32768), adig.data_ptr(), 2 * nk, p_rows, dig.data_ptr(),
+                         expo.data_ptr(), n_loc, n_sel, pitch, dst, ldp, eng.project_impl, eng.stream())
+        if j >= 1:
+            transform(j - 1)
+        done = torch.cuda.Event()
+        done.record(main)
+        comm.wait_event(done)
+        with torch.cuda.stream(comm):
+            _stream_fence(eng.device, group)          # every rank's stores of chunk j (and its FFT of j - 1) are done
+            fences[j] = torch.cuda.Event()
+            fences[j].record(comm)
+    transform(n_chunks - 1)
+    if host_out is not None:
+        for b in chunk_bufs:
+            b.record_stream(eng.copy_stream)
+    return True, out
+
+
+last_path: Optional[str] = None      # which path the last sharded_sed_on_device / calculate_sharded call took
+
+
+def frames_mode() -> bool:
+    """Frame-sharded multi-GPU path on (default) or off (``PSA_B200_SHARD=k``: all-gather the digit planes, shard k)."""
+    return os.environ.get("PSA_B200_SHARD", "frames").lower() != "k"
+
+
+def sharded_sed_on_device(calc, k_vecs: np.ndarray, proj_groups, complex_out: bool, local_rows=None, group=None,
+                          k_chunk_size: int = 500) -> torch.Tensor:
+    """This rank's k-slice ``shard_range(n_k, rank, N)`` of the SED, device-resident, from a trajectory whose frames
+    are spread over the ranks: :func:`frame_sharded_sed` when it can run, else :func:`sliced_ingest` + the one-GPU
+    pipeline on the slice.  (What ``bench.py`` times as ``value`` on several GPUs.)"""
+    from .engine import sed_on_device
+    global last_path
+    if frames_mode():
+        ok, out = frame_sharded_sed(calc, k_vecs, proj_groups, complex_out, local_rows, group, k_chunk_size=k_chunk_size)
+        if ok:
+            last_path = "frames"
+            return out
+    last_path = "k"
+    sliced_ingest(calc, proj_groups, local_rows, group)
+    k0, k1 = shard_range(int(k_vecs.shape[0]), dist.get_rank(group), dist.get_world_size(group))
+    return sed_on_device(calc.device_trajectory, k_vecs[k0:k1], proj_groups, complex_out, calc.use_displacements,
+                         k_chunk=k_chunk_size)
 
 
 def shared_result(calc, shape, np_dtype, src: int = 0, group=None) -> SharedHostArray:
@@ -457,8 +762,19 @@ def calculate_sharded(calc, k_points_mags: np.ndarray, k_vectors_3d: np.ndarray,
         shape = (n_t, n_k, 3) if complex_out else (n_t, n_k)
         shared = shared_result(calc, shape, np.complex64 if complex_out else np.float32, src, group)
         mark("start")
+        k0, k1 = shard_range(n_k, rank, world)
+        # 0. frames spread over the ranks and a shared result array: nothing but projections crosses NVLink
+        streamed = False
+        if ingest == "sliced" and frames_mode() and shared.available and n_t > 0:
+            streamed, _ = frame_sharded_sed(calc, k_vecs, proj_groups, complex_out, local_rows, group,
+                                            host_out=HostTarget(shared.ptr, n_k, k0, n_t, shared), marks=mark,
+                                            k_chunk_size=k_chunk_size)
         # 1. k-independent state on every rank
-        if ingest == "sliced":
+        global last_path
+        last_path = "frames" if streamed else "k"
+        if streamed:
+            pass
+        elif ingest == "sliced":
             sliced_ingest(calc, proj_groups, local_rows, group, marks=mark)
         else:
             tensors: List[Optional[torch.Tensor]] = []
@@ -477,7 +793,6 @@ def calculate_sharded(calc, k_points_mags: np.ndarray, k_vectors_3d: np.ndarray,
             mark("ingest_broadcast")
 
         # 2. every rank: its contiguous k-slice, no communication; spectra stream out over this rank's own PCIe link
-        k0, k1 = shard_range(n_k, rank, world)
         if not shared.available:
             # no shared segment on this box: the slices are gathered on the source GPU and leave through its link
             local = sed_on_device(dtraj, k_vecs[k0:k1], proj_groups, complex_out, calc.use_displacements,
@@ -487,7 +802,7 @@ def calculate_sharded(calc, k_points_mags: np.ndarray, k_vectors_3d: np.ndarray,
                 return None
             return SED(calc._to_host(full), np.fft.fftfreq(n_t, d=calc.dt_ps), k_points_mags, k_vectors_3d,
                        k_grid_shape=k_grid_shape, is_complex=complex_out, phase=None, context=calc._context(groups))
-        if k1 > k0 and n_t > 0:
+        if k1 > k0 and n_t > 0 and not streamed:
             sed_on_device(dtraj, k_vecs[k0:k1], proj_groups, complex_out, calc.use_displacements, k_chunk=k_chunk_size,
                           host_out=HostTarget(shared.ptr, n_k, k0, n_t, shared))
         mark("compute")

@@ -17,6 +17,7 @@ by ``psa_b200.dist.sliced_ingest``).
 """
 from __future__ import annotations
 
+import ctypes
 import hashlib
 import os
 import threading
@@ -32,6 +33,14 @@ from . import _lib
 K_CHUNK_CAP = max(8, min(1024, int(os.environ.get("PSA_B200_K_CHUNK", "1024"))))
 K_CHUNK_REFERENCE_DEFAULT = 500   # the reference's default k_chunk_size (sed_calculator.py:185)
 _UPLOAD_CHUNK_BYTES = 256 << 20   # pinned staging buffers for uploads from pageable / memory-mapped arrays
+
+
+# Streamed ingest (one GPU, velocities still in host memory): planning constants only - how many leading k-chunks are
+# projected frame range by frame range while the rest of the array is still crossing PCIe.  Results do not depend on them.
+_STREAM_MIN_BYTES = int(os.environ.get("PSA_B200_STREAM_MIN_MB", "256")) << 20
+_STREAM_H2D_RATE = {True: 50e9, False: 10e9}       # bytes/s from page-locked / pageable host memory
+_STREAM_PROJECT_RATE = 2.7e13                      # (k, frame, atom) triples per second of the projection kernel
+_STREAM_P_BYTES = 8 << 30                          # ceiling for the projection buffer of the streamed chunks
 
 
 def effective_k_chunk(k_chunk_size: int, n_k: int) -> int:
@@ -120,6 +129,7 @@ class Engine:
         self._comm_stream: Optional[torch.cuda.Stream] = None
         self.launches = 0          # kernels launched through this engine (bench reports it)
         self.profile: Optional[Dict[str, List[Tuple[torch.cuda.Event, torch.cuda.Event, int]]]] = None
+        self.timeline: Optional[List[Tuple[str, "torch.cuda.Event"]]] = None   # stage marks of one call (bench breakdown)
 
     # -- helpers
     def stream(self) -> int:
@@ -135,8 +145,8 @@ class Engine:
     @property
     def comm_stream(self) -> "torch.cuda.Stream":
         """Side stream of the multi-GPU exchange (peer stores + fences run under the first chunk's projection)."""
-        if self._comm_stream is None:
-            self._comm_stream = torch.cuda.Stream(device=self.device)
+        if self._comm_stream is None:          # high priority: its small kernels take the first SM that frees up
+            self._comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
         return self._comm_stream
 
     @property
@@ -166,6 +176,19 @@ class Engine:
         _lib.call(kernel, *args)
         end.record(stream)
         self.profile.setdefault(kernel, []).append((start, end, n_launches))
+
+    def mark(self, label: str, stream: Optional["torch.cuda.Stream"] = None) -> None:
+        """With ``self.timeline`` set: a timing event on ``stream`` (default: the current one) under ``label``."""
+        if self.timeline is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream if stream is not None else torch.cuda.current_stream(self.device))
+            self.timeline.append((label, ev))
+
+    def timeline_ms(self) -> List[Tuple[str, float]]:
+        """``[(label, ms since the first mark)]`` of the marks collected so far (synchronises the device)."""
+        torch.cuda.synchronize(self.device)
+        marks = self.timeline or []
+        return [(label, marks[0][1].elapsed_time(ev)) for label, ev in marks]
 
     def profile_summary(self) -> Dict[str, Dict[str, float]]:
         """{kernel: {ms, calls, launches}} from the events collected while ``self.profile`` was set."""
@@ -269,6 +292,18 @@ class Engine:
         return out
 
 
+class IngestStream:
+    """Frame ranges ``(t0, t1, event)`` of digit planes that are produced while they are consumed: iterating performs
+    the next host->device copy + digitise launch on a side stream and yields the event that marks the range valid.
+    ``seconds``: planning estimate of the whole transfer."""
+
+    def __init__(self, ranges, seconds: float):
+        self._ranges, self.seconds = ranges, float(seconds)
+
+    def __iter__(self):
+        return self._ranges
+
+
 class DeviceTrajectory:
     """A trajectory resident in HBM plus everything derived from it that is k-independent."""
 
@@ -287,6 +322,7 @@ class DeviceTrajectory:
         self._mean: Optional[torch.Tensor] = None
         self._groups: Dict[Tuple, Tuple] = {}
         self._arrivals: Dict[int, List[Tuple[int, int, Optional["torch.cuda.Event"]]]] = {}
+        self._frame_local: Dict[str, Any] = {}      # frame-sharded multi-GPU: digit planes of this rank's frames only
         self._indices: Dict[Optional[str], torch.Tensor] = {}
         self._lock = threading.RLock()
         self.h2d_bytes = 0
@@ -382,6 +418,7 @@ class DeviceTrajectory:
             self._mean = None
             self._groups.clear()
             self._arrivals.clear()
+            self._frame_local.clear()
 
     @property
     def mean(self) -> torch.Tensor:
@@ -419,7 +456,9 @@ class DeviceTrajectory:
         n_sel = self.n_a if idx is None else int(idx.size)
         with self._lock:
             self._groups[key] = (idx_dev, n_sel, int(dig.shape[-1]), dig, expo)
-            if arrivals:
+            if isinstance(arrivals, IngestStream):
+                self._arrivals[dig.data_ptr()] = arrivals
+            elif arrivals:
                 self._arrivals[dig.data_ptr()] = list(arrivals)
             else:
                 self._arrivals.pop(dig.data_ptr(), None)
@@ -428,12 +467,101 @@ class DeviceTrajectory:
         with self._lock:
             return self._arrivals.pop(dig.data_ptr(), None)
 
-    def prepare(self, groups: Sequence[Optional[np.ndarray]], use_displacements: bool) -> Tuple[torch.Tensor, List[Tuple]]:
+    def prepare(self, groups: Sequence[Optional[np.ndarray]], use_displacements: bool,
+                stream: bool = False) -> Tuple[torch.Tensor, List[Tuple]]:
         """Mean positions and the digit planes of every group (both cached).  Running the two passes on
         separate streams was measured (profiles/, round 1): both are HBM-bound and the pair gained < 3 %,
-        so they stay on one stream, which also keeps per-kernel timings clean."""
+        so they stay on one stream, which also keeps per-kernel timings clean.  ``stream``: the caller consumes
+        frame ranges in arrival order (:func:`sed_on_device`), see :meth:`_start_stream`."""
         mean = self.mean
+        if stream and not use_displacements:
+            self._start_stream(groups)
         return mean, [self.group(g, use_displacements) for g in groups]
+
+    def _start_stream(self, groups: Sequence[Optional[np.ndarray]]) -> None:
+        """Velocity mode, raw velocities still in host memory: instead of one upload followed by one digitise pass,
+        hand the groups an :class:`IngestStream` - frame ranges are copied and digitised on a side stream one by one
+        and the first projection consumes them in that order, so the tensor cores work while PCIe is still busy.
+        (Displacements need the final mean, i.e. every position, before the first row can be digitised.)"""
+        if os.environ.get("PSA_B200_STREAM_INGEST", "1") == "0" or "vel" in self._dev:
+            return
+        host = self._host["vel"]
+        if isinstance(host, torch.Tensor):
+            if host.is_cuda or host.dtype != torch.float32 or not host.is_contiguous():
+                return
+            src = host
+        else:
+            arr = np.asarray(host)
+            if arr.dtype != np.float32 or not arr.flags.c_contiguous:
+                return
+            src = torch.from_numpy(arr)
+        n_t, n_a = self.n_t, self.n_a
+        if src.numel() * 4 < _STREAM_MIN_BYTES or n_t < 1024:
+            return
+        with self._lock:
+            keyed = [self._group_key(g, False) for g in groups]
+            if any(key in self._groups for key, _ in keyed):
+                return
+            eng = self.engine
+            pinned = src.is_pinned()
+            main, ingest = torch.cuda.current_stream(eng.device), eng.comm_stream
+            dev = torch.empty(src.shape, dtype=torch.float32, device=eng.device)
+            weight = self.weight
+            planes = []
+            for key, idx in keyed:
+                idx_dev = None if idx is None else self._index_tensor(key, idx)
+                n_sel = n_a if idx is None else int(idx.size)
+                pitch = int(_lib.load().psa_pitch(n_sel))
+                dig = eng.empty((3, 4, n_t, pitch), torch.int8)
+                expo = eng.empty((3, n_t), torch.int32)
+                planes.append((key, idx_dev, n_sel, pitch, dig, expo))
+            ingest.wait_stream(main)            # buffers handed over by the allocator may still be in use on `main`
+            for t in [dev] + [p[4] for p in planes] + [p[5] for p in planes]:
+                t.record_stream(ingest)
+            step = max(256, -(-n_t // 16) // 256 * 256)           # ~16 ranges, whole 256-frame projection tiles
+
+            def ranges():
+                flat_src, flat_dst = src.view(-1), dev.view(-1)
+                row = n_a * 3
+                sub = max(1, _UPLOAD_CHUNK_BYTES // 4)
+                bufs, events = None, [None, None]
+                if not pinned:
+                    bufs = [torch.empty(min(sub, flat_src.numel()), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+                n_sub = 0
+                for t0 in range(0, n_t, step):
+                    t1 = min(n_t, t0 + step)
+                    with torch.cuda.stream(ingest):
+                        if pinned:
+                            dev[t0:t1].copy_(src[t0:t1], non_blocking=True)
+                        else:
+                            for off in range(t0 * row, t1 * row, sub):
+                                n = min(sub, t1 * row - off)
+                                b = n_sub & 1
+                                n_sub += 1
+                                if events[b] is not None:
+                                    events[b].synchronize()
+                                np.copyto(bufs[b].numpy()[:n], flat_src[off:off + n].numpy())
+                                flat_dst[off:off + n].copy_(bufs[b][:n], non_blocking=True)
+                                events[b] = torch.cuda.Event()
+                                events[b].record(ingest)
+                        rows = dev[t0:t1]
+                        for _, idx_dev, n_sel, pitch, dig, expo in planes:
+                            own = ((ctypes.c_void_p * 1)(dig.data_ptr()), (ctypes.c_void_p * 1)(expo.data_ptr()))
+                            # the 128-thread launch shares the SMs with the projection kernel of the previous range
+                            eng._run("psa_digitize_rows_peers", 1, rows.data_ptr(), None, _ptr(weight), _ptr(idx_dev),
+                                     t1 - t0, n_a, n_sel, pitch, ctypes.addressof(own[0]), ctypes.addressof(own[1]), 1,
+                                     n_t, t0, 1, eng.stream())
+                        ev = torch.cuda.Event()
+                        ev.record(ingest)
+                        eng.mark("range_on_device", ingest)
+                    yield t0, t1, ev
+                self._dev["vel"] = dev
+                self.h2d_bytes += src.numel() * 4
+
+            sched = IngestStream(ranges(), src.numel() * 4 / _STREAM_H2D_RATE[pinned])
+            for key, idx_dev, n_sel, pitch, dig, expo in planes:
+                self._groups[key] = (idx_dev, n_sel, pitch, dig, expo)
+                self._arrivals[dig.data_ptr()] = sched
 
     def group(self, idx: Optional[np.ndarray], use_displacements: bool) -> Tuple:
         """``(idx_dev|None, n_sel, pitch, digits, exponents)`` for an atom selection (cached)."""
@@ -483,20 +611,41 @@ def sed_on_device(traj: DeviceTrajectory, k_vecs: np.ndarray, groups: Sequence[O
     out = None if host_out is not None else torch.empty(shape, dtype=dtype, device=eng.device)
     if n_k == 0:
         return out
-    mean, entries = traj.prepare(groups, use_displacements)
+    eng.mark("start")
+    mean, entries = traj.prepare(groups, use_displacements, stream=True)
+    eng.mark("ingest")                      # positions + mean (+ velocities + digit planes unless they are streamed)
     arrivals = [traj.pop_arrivals(e[3]) for e in entries]
-    hint = None
-    if any(arrivals):                       # a multi-GPU exchange is still in flight: first chunk goes range by range
+    ldp = (n_t + 3) // 4 * 4
+    # Chunks whose projection runs frame range by frame range, in the order in which the digit planes become valid:
+    # * one GPU, velocities still crossing PCIe (IngestStream shared by all groups): as many leading chunks as the
+    #   tensor cores can project during the transfer, frames outermost;
+    # * a multi-GPU exchange in flight on a side stream (one list of ranges per group): the first chunk.
+    shared = arrivals[0] if arrivals and isinstance(arrivals[0], IngestStream) else None
+    n_prefix = 0
+    if shared is not None:
+        assert all(a is shared for a in arrivals)
+        chunks = plan_k_chunks(n_k, k_chunk)
+        per_k = n_t * sum(e[1] for e in entries) / _STREAM_PROJECT_RATE
+        k_budget, k_sum = 0.85 * shared.seconds / per_k, 0
+        for _, nk in chunks:
+            p_bytes = len(entries) * 2 * (k_sum + nk) * 3 * ldp * 4
+            if n_prefix and (k_sum + nk / 2 > k_budget or p_bytes > _STREAM_P_BYTES):
+                break
+            n_prefix, k_sum = n_prefix + 1, k_sum + nk
+    elif any(arrivals):
         longest = max(t1 - t0 for arr in arrivals if arr for t0, t1, _ in arr)
-        hint = (longest, eng.n_clusters)
-    chunks = plan_k_chunks(n_k, k_chunk, hint)
+        chunks = plan_k_chunks(n_k, k_chunk, (longest, eng.n_clusters))
+        n_prefix = 1
+    else:
+        chunks = plan_k_chunks(n_k, k_chunk)
     kc = max(nk for _, nk in chunks)
+    k_prefix = sum(nk for _, nk in chunks[:n_prefix])
     window = traj.window
     rows_alloc = 2 * kc
-    ldp = (n_t + 3) // 4 * 4
+    p_rows = 2 * max(kc, k_prefix)
     kv_dev = eng.upload_small(np.ascontiguousarray(k_vecs, np.float32))
-    P = eng.empty((len(entries), rows_alloc, 3, ldp), torch.float32)
-    group_stride = rows_alloc * 3 * ldp
+    P = eng.empty((len(entries), p_rows, 3, ldp), torch.float32)
+    group_stride = p_rows * 3 * ldp
     adig_bufs: Dict[int, torch.Tensor] = {}
     mode = _lib.MODE_COHERENT if complex_out else _lib.MODE_INCOHERENT
     if host_out is not None:
@@ -505,27 +654,49 @@ def sed_on_device(traj: DeviceTrajectory, k_vecs: np.ndarray, groups: Sequence[O
         drained = [None, None]                                           # copy-stream events per buffer
         compute, copy = torch.cuda.current_stream(eng.device), eng.copy_stream
     main = torch.cuda.current_stream(eng.device)
-    for ci, (k0, nk) in enumerate(chunks):
-        for g, (idx_dev, n_sel, pitch, dig, expo) in enumerate(entries):
-            adig = adig_bufs.get(pitch)
-            if adig is None:
-                adig = adig_bufs[pitch] = eng.empty((4, rows_alloc, pitch), torch.int8)
-            eng.phase_digits(kv_dev[k0:k0 + nk], mean, idx_dev, n_sel, pitch, rows_alloc, out=adig)
-            if ci == 0 and arrivals[g]:
-                for t0, t1, ev in arrivals[g]:            # frames in the order in which the peers' rows land
-                    if ev is not None:
-                        main.wait_event(ev)
-                    if t1 > t0:
-                        eng.project(adig, 2 * nk, rows_alloc, dig, expo, n_t, n_sel, pitch, P[g], ldp, t_range=(t0, t1))
+    if n_prefix:
+        try:
+            adig_pre = []
+            for idx_dev, n_sel, pitch, dig, expo in entries:
+                adig_pre.append(eng.phase_digits(kv_dev[:k_prefix], mean, idx_dev, n_sel, pitch, 2 * k_prefix))
+            if shared is not None:
+                for t0, t1, ev in shared:                     # iterating issues the next copy + digitise launch
+                    main.wait_event(ev)
+                    for g, (idx_dev, n_sel, pitch, dig, expo) in enumerate(entries):
+                        eng.project(adig_pre[g], 2 * k_prefix, 2 * k_prefix, dig, expo, n_t, n_sel, pitch, P[g], ldp,
+                                    t_range=(t0, t1))
             else:
+                for g, (idx_dev, n_sel, pitch, dig, expo) in enumerate(entries):
+                    for t0, t1, ev in arrivals[g] or [(0, n_t, None)]:   # frames in the order the peers' rows land
+                        if ev is not None:
+                            main.wait_event(ev)
+                        if t1 > t0:
+                            eng.project(adig_pre[g], 2 * k_prefix, 2 * k_prefix, dig, expo, n_t, n_sel, pitch, P[g], ldp,
+                                        t_range=(t0, t1))
+            del adig_pre
+            eng.mark("prefix_projected")
+        except BaseException:
+            traj.reset_derived()                              # half-filled digit planes must not be reused
+            raise
+    for ci, (k0, nk) in enumerate(chunks):
+        Pc = P
+        if ci < n_prefix:
+            Pc = P[:, 2 * k0:]                                # projected above; same group stride
+        else:
+            for g, (idx_dev, n_sel, pitch, dig, expo) in enumerate(entries):
+                adig = adig_bufs.get(pitch)
+                if adig is None:
+                    adig = adig_bufs[pitch] = eng.empty((4, rows_alloc, pitch), torch.int8)
+                eng.phase_digits(kv_dev[k0:k0 + nk], mean, idx_dev, n_sel, pitch, rows_alloc, out=adig)
                 eng.project(adig, 2 * nk, rows_alloc, dig, expo, n_t, n_sel, pitch, P[g], ldp)
         if host_out is None:
-            eng.fft_sed(P, len(entries), group_stride, nk, n_t, ldp, mode, out, n_k, k0, window)
+            eng.fft_sed(Pc, len(entries), group_stride, nk, n_t, ldp, mode, out, n_k, k0, window)
             continue
         buf = chunk_bufs[ci & 1]
         if drained[ci & 1] is not None:
             compute.wait_event(drained[ci & 1])                          # its previous contents are on the host
-        eng.fft_sed(P, len(entries), group_stride, nk, n_t, ldp, mode, buf, kc, 0, window)
+        eng.fft_sed(Pc, len(entries), group_stride, nk, n_t, ldp, mode, buf, kc, 0, window)
+        eng.mark("chunk_transformed")
         ready = torch.cuda.Event()
         ready.record(compute)
         copy.wait_event(ready)
@@ -533,6 +704,7 @@ def sed_on_device(traj: DeviceTrajectory, k_vecs: np.ndarray, groups: Sequence[O
                   buf.data_ptr(), kc * elem, nk * elem, n_rows, copy.cuda_stream)
         drained[ci & 1] = torch.cuda.Event()
         drained[ci & 1].record(copy)
+        eng.mark("chunk_on_host", copy)
     if host_out is not None:
         for b in chunk_bufs:                     # the copy stream still reads them: keep the allocator from reusing
             b.record_stream(copy)

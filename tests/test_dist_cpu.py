@@ -21,6 +21,28 @@ def test_shard_range_partitions_exactly(n, world):
     assert max(widths) - min(widths) <= 1 and sum(widths) == n
 
 
+@pytest.mark.parametrize("n_k,world,cap", [(10000, 8, 2048), (10000, 2, 2048), (1000, 8, 2048), (37, 2, 3), (5, 8, 2048),
+                                           (200, 4, 64)])
+def test_frame_shard_plan_covers_every_k_once(n_k, world, cap):
+    """Frame-sharded multi-GPU plan: the owners' slices are the k-sharded layout, their chunks tile them exactly, no
+    chunk exceeds the cap, and at every (chunk, step) the ranks write to pairwise different owners (one stream per
+    NVLink port: rank r works for owner r + s at step s)."""
+    slices, n_chunks, chunk = pdist.frame_shard_plan(n_k, world, cap)
+    assert slices == [pdist.shard_range(n_k, q, world) for q in range(world)]
+    seen = np.zeros(n_k, np.int64)
+    for q in range(world):
+        pieces = [chunk(q, j) for j in range(n_chunks)]
+        assert pieces[0][0] == slices[q][0] and pieces[-1][1] == slices[q][1]
+        for (a, b), (c, d) in zip(pieces[:-1], pieces[1:]):
+            assert b == c
+        for a, b in pieces:
+            assert 0 <= b - a <= cap
+            seen[a:b] += 1
+    assert np.all(seen == 1)
+    for s_ in range(world):
+        assert sorted((r + s_) % world for r in range(world)) == list(range(world))
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

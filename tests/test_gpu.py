@@ -231,6 +231,45 @@ def test_first_chunk_follows_an_arrival_schedule(gold_si):
     assert dtraj.pop_arrivals(dig) is None                                   # consumed
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_streamed_ingest_is_bit_identical(monkeypatch, pinned):
+    """One GPU, velocities still in host memory: frame ranges are copied + digitised on a side stream while the leading
+    k-chunks are projected range by range (engine.IngestStream).  Same bits as upload-then-compute, for page-locked and
+    pageable sources, one and two atom groups, several streamed chunks and a ragged last range."""
+    from psa_b200 import SEDCalculator, Trajectory
+    from psa_b200 import engine as E
+    spec = synth.si_spec("stream", 5, 2304 + 100, seed=5)                # 1000 atoms, 2404 frames: 10 ranges, last ragged
+    traj = spec.trajectory()
+    pos, vel = traj.positions, traj.velocities
+    if pinned:
+        pos_t, vel_t = torch.from_numpy(pos).pin_memory(), torch.from_numpy(vel).pin_memory()
+        traj = Trajectory(pos_t.numpy(), vel_t.numpy(), traj.types, traj.timesteps, traj.box_matrix, traj.box_lengths,
+                          traj.box_tilts, traj.dt_ps)
+    calc = SEDCalculator(traj, *spec.cells)
+    mags, kv = calc.get_k_path([1, 1, 0], 2.0, 150)
+    cases = [dict(summation_mode="coherent", k_chunk_size=40),                              # 4 chunks of <= 40
+             dict(summation_mode="incoherent", basis_atom_types=[1, 2], k_chunk_size=64),   # two groups
+             dict(summation_mode="coherent", basis_atom_indices=list(range(0, 1000, 3)))]   # gathered selection, 1 chunk
+    monkeypatch.setenv("PSA_B200_STREAM_INGEST", "0")
+    want = []
+    for kw in cases:
+        calc.release_device_memory()
+        want.append(calc.calculate(mags, kv, **kw).sed)
+    monkeypatch.setenv("PSA_B200_STREAM_INGEST", "1")
+    monkeypatch.setattr(E, "_STREAM_MIN_BYTES", 1 << 20)
+    monkeypatch.setattr(E, "_UPLOAD_CHUNK_BYTES", 1 << 20)               # several staging pieces per range (pageable)
+    for rate in (2.7e13, 2.7e10):                                        # every chunk / only the first one streamed
+        monkeypatch.setattr(E, "_STREAM_PROJECT_RATE", rate)
+        for kw, w in zip(cases, want):
+            calc.release_device_memory()
+            launches = calc.engine.launches
+            got = calc.calculate(mags, kv, **kw).sed
+            np.testing.assert_array_equal(got, w)
+            assert calc.device_trajectory._dev.get("vel") is not None    # the raw array ended up resident as usual
+            assert calc.engine.launches - launches > 10                   # range-by-range launches really happened
+            np.testing.assert_array_equal(calc.calculate(mags, kv, **kw).sed, w)      # cached planes afterwards
+
+
 def test_project_extreme_digits_no_overflow(eng):
     """Worst-case digits (every product at its maximum) over a full 32768-atom pass stay exact."""
     from psa_b200 import _lib
@@ -849,8 +888,10 @@ def test_k_sharded_two_gpus_equals_single_gpu():
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     import re as _re
     m = _re.search(r"MULTIGPU_CHECK world=2 results=\[([^\]]*)\]", out.stdout)
-    # 3 broadcast-ingest cases + 8 sliced-ingest cases (even / ragged frame split x velocity / displacement x 2 modes)
-    assert m and m.group(1).split(", ") == ["True"] * 11, out.stdout[-2000:]
+    # 3 broadcast-ingest cases + sliced-ingest cases: {frame-sharded, k-sharded} x {velocity, displacement} x 3 calls x
+    # {first call, second call on the cached state} on an even frame split, the same on a ragged split (fallback path)
+    got = m.group(1).split(", ") if m else []
+    assert len(got) == 39 and got == ["True"] * 39, out.stdout[-2000:]
 
 
 def test_npy_cache_streams_to_device(gold_si, tmp_path):
