@@ -402,8 +402,10 @@ class SEDCalculator:
                 num, den = 0.0, 0
                 mom = eng.empty((2,), torch.float64)
                 for g in recon_groups:
-                    idx_dev = eng.upload_small(np.ascontiguousarray(g, np.int32))
-                    eng._run("psa_disp_moments", 1, dtraj.positions.data_ptr(), mean.data_ptr(), idx_dev.data_ptr(),
+                    whole = g.size == n_atoms and np.array_equal(g, np.arange(n_atoms))   # whole rows: vector loads
+                    idx_dev = None if whole else eng.upload_small(np.ascontiguousarray(g, np.int32))
+                    eng._run("psa_disp_moments", 1, dtraj.positions.data_ptr(), mean.data_ptr(),
+                             None if whole else idx_dev.data_ptr(),
                              traj.n_frames, n_atoms, int(g.size), mom.data_ptr(), eng.stream())
                     s1, s2 = mom.cpu().tolist()
                     n_el = traj.n_frames * int(g.size) * 3

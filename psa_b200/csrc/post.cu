@@ -427,19 +427,42 @@ int launch_select_pass(const float* x, int64_t n, int done_bits, const uint32_t*
 // ---------------------------------------------------------------------------------------------
 // Reductions
 // ---------------------------------------------------------------------------------------------
-__global__ void disp_moments_kernel(const float* __restrict__ pos, const float* __restrict__ mean,
-                                    const int32_t* __restrict__ idx, int64_t n_t, int64_t n_a, int64_t n_sel,
-                                    double* __restrict__ out2) {
+// Sum and sum of squares (float64) of the float32 displacements pos - mean over (frame, selected atom, component).
+// grid.x tiles the columns of a frame row, grid.y the frames; a thread keeps its mean values in registers and walks
+// down the frames, so a warp reads 512 contiguous bytes per frame (whole rows: one float4 per thread) and there is no
+// index arithmetic in the loop.
+template <int kMode>   // 0: whole rows as float4 (n_a * 3 divisible by 4), 1: whole rows scalar, 2: gathered atoms
+__global__ void __launch_bounds__(256) disp_moments_kernel(const float* __restrict__ pos, const float* __restrict__ mean,
+                                                           const int32_t* __restrict__ idx, int64_t n_t, int64_t n_a,
+                                                           int64_t n_sel, int64_t t_per_block, double* __restrict__ out2) {
+  constexpr int kVals = kMode == 0 ? 4 : (kMode == 1 ? 1 : 3);
+  const int64_t row = n_a * 3;
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // float4 / float / selected atom
+  const int64_t n_items = kMode == 0 ? row / 4 : (kMode == 1 ? row : n_sel);
+  const int64_t t0 = (int64_t)blockIdx.y * t_per_block, t1 = t0 + t_per_block < n_t ? t0 + t_per_block : n_t;
   double s1 = 0., s2 = 0.;
-  const int64_t total = n_t * n_sel;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    int64_t t = e / n_sel, j = e % n_sel;
-    int64_t atom = idx ? (int64_t)__ldg(idx + j) : j;
+  if (item < n_items) {
+    const int64_t col = kMode == 0 ? item * 4 : (kMode == 1 ? item : (int64_t)__ldg(idx + item) * 3);
+    float m[kVals];
 #pragma unroll
-    for (int p = 0; p < 3; ++p) {
-      float d = __fsub_rn(__ldg(pos + (t * n_a + atom) * 3 + p), __ldg(mean + atom * 3 + p));
-      s1 += (double)d;
-      s2 += (double)d * (double)d;
+    for (int p = 0; p < kVals; ++p) m[p] = __ldg(mean + col + p);
+    const float* src = pos + t0 * row + col;
+#pragma unroll 8
+    for (int64_t t = t0; t < t1; ++t, src += row) {
+      float v[kVals];
+      if constexpr (kMode == 0) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(src));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
+#pragma unroll
+        for (int p = 0; p < kVals; ++p) v[p] = __ldg(src + p);
+      }
+#pragma unroll
+      for (int p = 0; p < kVals; ++p) {
+        const double d = (double)__fsub_rn(v[p], m[p]);
+        s1 += d;
+        s2 = fma(d, d, s2);
+      }
     }
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -456,9 +479,19 @@ int launch_disp_moments(const float* pos, const float* mean, const int32_t* idx,
                         int64_t n_sel, double* out2, cudaStream_t s) {
   PSA_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(double), s));
   if (n_t * n_sel == 0) return PSA_OK;
-  int64_t blocks = (n_t * n_sel + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  disp_moments_kernel<<<(unsigned)blocks, 256, 0, s>>>(pos, mean, idx, n_t, n_a, n_sel, out2);
+  const int64_t row = n_a * 3;
+  const bool vec = idx == nullptr && (row & 3) == 0 && ((uintptr_t)pos & 15) == 0 && ((uintptr_t)mean & 15) == 0;
+  const int64_t n_items = idx != nullptr ? n_sel : (vec ? row / 4 : row);
+  const int64_t bx = (n_items + 255) / 256;
+  int64_t by = (148 * 8 + bx - 1) / bx;                     // ~8 CTAs per SM in total
+  if (by > n_t) by = n_t;
+  if (by > 65535) by = 65535;
+  const int64_t t_per_block = (n_t + by - 1) / by;
+  by = (n_t + t_per_block - 1) / t_per_block;
+  const dim3 grid((unsigned)bx, (unsigned)by);
+  if (idx != nullptr) disp_moments_kernel<2><<<grid, 256, 0, s>>>(pos, mean, idx, n_t, n_a, n_sel, t_per_block, out2);
+  else if (vec) disp_moments_kernel<0><<<grid, 256, 0, s>>>(pos, mean, idx, n_t, n_a, n_sel, t_per_block, out2);
+  else disp_moments_kernel<1><<<grid, 256, 0, s>>>(pos, mean, idx, n_t, n_a, n_sel, t_per_block, out2);
   return launch_status("disp_moments_kernel");
 }
 

@@ -437,6 +437,7 @@ def sliced_ingest(calc, proj_groups, local_rows=None, group=None, marks=None, pi
 
 # ---------------------------------------------------------------------------------------------- frame-sharded path
 FRAME_K_CAP = 2048        # k-points per projection launch of the frame-sharded path (one owner's chunk)
+FRAME_K_CAP_STREAMED = 1024   # ... when the chunks stream out to host memory while the next one is projected
 
 
 class PeerBuffers:
@@ -565,7 +566,11 @@ def frame_sharded_sed(calc, k_vecs: np.ndarray, proj_groups, complex_out: bool, 
     bounds = [shard_range(n_t, r, world) for r in range(world)]
     if any(a % 4 or b <= a for a, b in bounds) or n_k == 0:
         return False, None
-    k_cap = FRAME_K_CAP if k_chunk_size >= 500 else max(1, int(k_chunk_size))
+    # device-resident result: big launches (whole waves of projection tiles) and the FFT of a chunk issued one chunk
+    # late, so that nobody ever waits for the fence; streamed to the host: smaller chunks, transformed as soon as
+    # their frames have landed - every copy starts one chunk earlier and the tail after the last projection is short
+    lag = 1 if host_out is None else 0
+    k_cap = (FRAME_K_CAP if lag else FRAME_K_CAP_STREAMED) if k_chunk_size >= 500 else max(1, int(k_chunk_size))
     slices, n_chunks, chunk = frame_shard_plan(n_k, world, k_cap)
     kc = max(chunk(q, j)[1] - chunk(q, j)[0] for q in range(world) for j in range(n_chunks))
     n_groups = len(proj_groups)
@@ -661,7 +666,7 @@ def frame_sharded_sed(calc, k_vecs: np.ndarray, proj_groups, complex_out: bool, 
                 dst = bufs.ptrs[j % 3][q] + 4 * (g * group_stride + f0)
                 eng._run("psa_project", -(-n_sel // 32768), adig.data_ptr(), 2 * nk, p_rows, dig.data_ptr(),
                          expo.data_ptr(), n_loc, n_sel, pitch, dst, ldp, eng.project_impl, eng.stream())
-        if j >= 1:
+        if lag and j >= 1:
             transform(j - 1)
         done = torch.cuda.Event()
         done.record(main)
@@ -670,7 +675,10 @@ def frame_sharded_sed(calc, k_vecs: np.ndarray, proj_groups, complex_out: bool, 
             _stream_fence(eng.device, group)          # every rank's stores of chunk j (and its FFT of j - 1) are done
             fences[j] = torch.cuda.Event()
             fences[j].record(comm)
-    transform(n_chunks - 1)
+        if not lag:
+            transform(j)
+    if lag:
+        transform(n_chunks - 1)
     if host_out is not None:
         for b in chunk_bufs:
             b.record_stream(eng.copy_stream)

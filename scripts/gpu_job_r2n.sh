@@ -17,5 +17,5 @@ PY
 }
 timeout 900 $TR --nproc-per-node 2 --master-port 29542 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2n_bench_c4_n2_frames.json 2> gpurun_out/r2n_bench_c4_n2_frames.err; echo "frames rc=$?"; show gpurun_out/r2n_bench_c4_n2_frames.json; tail -3 gpurun_out/r2n_bench_c4_n2_frames.err | cut -c1-300
 PSA_B200_SHARD=k timeout 900 $TR --nproc-per-node 2 --master-port 29543 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2n_bench_c4_n2_k.json 2> gpurun_out/r2n_bench_c4_n2_k.err; echo "k rc=$?"; show gpurun_out/r2n_bench_c4_n2_k.json
-timeout 300 python scripts/pcie_rates.py > gpurun_out/r2n_pcie_rates.log 2>&1; echo "pcie rc=$?"; cat gpurun_out/r2n_pcie_rates.log
-timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-ised --no-int8-peak > gpurun_out/r2n_bench_c4_n1.json 2> gpurun_out/r2n_bench_c4_n1.err; echo "n1 rc=$?"; show gpurun_out/r2n_bench_c4_n1.json
+
+

@@ -749,6 +749,28 @@ def test_batched_ised_matches_oracle_groups_auto_and_overlap():
         np.testing.assert_array_equal(x["frames"].cpu().numpy(), y["frames"])
 
 
+@pytest.mark.parametrize("n_t,n_a,gather", [(300, 64, False), (301, 37, False), (257, 50, True), (3, 5, False),
+                                             (1200, 1000, False)])
+def test_displacement_moments_every_load_path(eng, n_t, n_a, gather):
+    """sum and sum of squares of the float32 displacements (the 'auto' rescale of iSED, sed_calculator.py:506-512):
+    whole rows through 16-byte loads, whole rows of a length that is not a multiple of four, a gathered selection."""
+    from psa_b200 import _lib
+    rng = np.random.default_rng(n_t + n_a)
+    pos = (rng.random((n_t, n_a, 3)) * 30 + rng.standard_normal((n_t, n_a, 3)) * 0.07).astype(np.float32)
+    mean = np.mean(pos, axis=0, dtype=np.float32)
+    idx = np.sort(rng.choice(n_a, size=n_a // 3, replace=False)).astype(np.int32) if gather else None
+    sel = pos if idx is None else pos[:, idx]
+    d = (sel - (mean if idx is None else mean[idx])[None]).astype(np.float64)
+    out = torch.zeros(2, dtype=torch.float64, device=eng.device)
+    idx_dev = None if idx is None else dev(eng, idx)
+    _lib.call("psa_disp_moments", dev(eng, pos).data_ptr(), dev(eng, mean).data_ptr(),
+              None if idx is None else idx_dev.data_ptr(), n_t, n_a, n_a if idx is None else idx.size,
+              out.data_ptr(), eng.stream())
+    s1, s2 = out.cpu().tolist()
+    assert abs(s1 - d.sum()) <= 1e-9 * np.abs(d).sum() + 1e-12
+    assert abs(s2 - (d * d).sum()) <= 1e-12 * (d * d).sum()
+
+
 def test_mass_weighting_and_window_extensions():
     """README-level keywords the shipped source lacks: defaults reproduce the unweighted, unwindowed
     reference bit for bit; when given they follow the oracle's definition (float32 sqrt(m) v, taper before the FFT)."""
