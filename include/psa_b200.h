@@ -126,6 +126,16 @@ int psa_project_rows(const int8_t* adig, int64_t rows, int64_t rows_alloc, const
                      int64_t n_t, int64_t t0, int64_t n_t_rows, int64_t n_sel, int64_t pitch, float* P, int64_t ldp,
                      int impl, void* stream);
 
+/* psa_project on the tensor cores with a destination per ROW RANGE: rows [row_begin[q], row_begin[q + 1]) of the
+ * projection are stored as rows 0, 1, ... of dests[q] ([rows_q][3][ldp] float32; local or peer memory) instead of into
+ * one P.  dests[n_dest] and row_begin[n_dest + 1] are HOST arrays, 1 <= n_dest <= 8, row_begin[0] = 0,
+ * row_begin[n_dest] = rows.  A frame-sharded multi-GPU run projects a rank's frames for the k-points of ALL owners in one
+ * launch (whole waves of tiles, full-width tiles across owner boundaries) - the all-to-all that turns "frames per rank"
+ * into "k-points per rank" (the k-sharding of sed_calculator.py:287's chunk loop over ranks) is the epilogue's stores. */
+int psa_project_routed(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig, const int32_t* expo,
+                       int64_t n_t, int64_t n_sel, int64_t pitch, float* const* dests, const int64_t* row_begin,
+                       int n_dest, int64_t ldp, void* stream);
+
 /* FFT plan for n_t frames: twiddles, plus (when n_t is not a power of two) the Bluestein chirp and
  * its spectrum.  The caller owns the buffer: allocate psa_fft_plan_bytes(n_t) device bytes (-1 = n_t not
  * supported: 2 <= n_t <= 2^19), fill it once with psa_fft_plan_init, reuse it for every psa_fft_sed. */

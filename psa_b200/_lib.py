@@ -37,6 +37,8 @@ _SIGNATURES = {
                                  c_void_p, c_void_p]),
     "psa_project": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                             c_void_p, c_int64, c_int, c_void_p]),
+    "psa_project_routed": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p,
+                                   c_void_p, c_int, c_int64, c_void_p]),
     "psa_project_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
                                  c_void_p, c_int64, c_int, c_void_p]),
     "psa_fft_plan_bytes": (c_int64, [c_int64]),

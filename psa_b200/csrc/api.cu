@@ -206,6 +206,22 @@ int psa_project_rows(const int8_t* adig, int64_t rows, int64_t rows_alloc, const
   return PSA_ERR_BAD_ARG;
 }
 
+int psa_project_routed(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig, const int32_t* expo,
+                       int64_t n_t, int64_t n_sel, int64_t pitch, float* const* dests, const int64_t* row_begin,
+                       int n_dest, int64_t ldp, void* stream) {
+  PSA_REQUIRE(adig && bdig && expo && dests && row_begin, "psa_project_routed: null pointer");
+  PSA_REQUIRE(rows > 0 && rows <= rows_alloc && n_t > 0 && n_sel > 0, "psa_project_routed: bad extents");
+  PSA_REQUIRE(n_dest >= 1 && n_dest <= kMaxRouteDests, "psa_project_routed: 1 to %d destinations", kMaxRouteDests);
+  PSA_REQUIRE(pitch >= n_sel && pitch % 64 == 0, "psa_project_routed: pitch must be a multiple of 64 and >= n_sel");
+  PSA_REQUIRE(ldp >= n_t && ldp % 4 == 0, "psa_project_routed: ldp must be a multiple of 4 and >= n_t");
+  PSA_REQUIRE(((uintptr_t)adig % 16) == 0 && ((uintptr_t)bdig % 16) == 0, "psa_project_routed: buffers must be 16-byte aligned");
+  for (int q = 0; q < n_dest; ++q)
+    PSA_REQUIRE(((uintptr_t)dests[q] % 16) == 0, "psa_project_routed: destination %d must be 16-byte aligned", q);
+  DeviceGuard guard(adig);       // the destinations may be peer GPUs' buffers; the digits are always local
+  return launch_project_tc2(adig, rows, rows_alloc, bdig, expo, n_t, n_t, n_sel, pitch, nullptr, ldp, as_stream(stream),
+                            dests, row_begin, n_dest);
+}
+
 int psa_project(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig, const int32_t* expo,
                 int64_t n_t, int64_t n_sel, int64_t pitch, float* P, int64_t ldp, int impl, void* stream) {
   return psa_project_rows(adig, rows, rows_alloc, bdig, expo, n_t, 0, n_t, n_sel, pitch, P, ldp, impl, stream);

@@ -100,9 +100,13 @@ int launch_digitize(const float* data, const float* mean, const float* weight, c
                     int64_t n_a, int64_t n_sel, int64_t pitch, int8_t* dig, int32_t* expo, cudaStream_t s);
 int launch_phase_digits(const float* kvecs, int64_t n_k, const float* mean, const int32_t* idx,
                         int64_t n_sel, int64_t pitch, int64_t rows_alloc, int8_t* adig, cudaStream_t s);
+// dests / row_begin / n_dest (host arrays): rows [row_begin[q], row_begin[q + 1]) are stored as rows 0.. of dests[q]
+// instead of into P (frame-sharded multi-GPU run: one launch for every owner's k-points); n_dest == 0: everything into P
+constexpr int kMaxRouteDests = 8;
 int launch_project_tc2(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig,
                        const int32_t* expo, int64_t n_t, int64_t n_t_total, int64_t n_sel, int64_t pitch, float* P,
-                       int64_t ldp, cudaStream_t s);
+                       int64_t ldp, cudaStream_t s, float* const* dests = nullptr, const int64_t* row_begin = nullptr,
+                       int n_dest = 0);
 int launch_project_simt(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig,
                         const int32_t* expo, int64_t n_t, int64_t n_t_total, int64_t n_sel, int64_t pitch, float* P,
                         int64_t ldp, cudaStream_t s);

@@ -165,10 +165,21 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, int r_tiles, int t_ti
   return c;
 }
 
+// Where the projection rows go.  n == 0: all of them into P (row r at P + r * 3 * ldp).  n > 0 (frame-sharded multi-GPU
+// run): rows [begin[q], begin[q + 1]) belong to destination q - another rank's projection buffer, mapped through CUDA
+// IPC - and land there as its rows 0, 1, ...: ONE launch projects this rank's frames for every owner's k-points.
+struct RowRoute {
+  float* base[kMaxRouteDests];
+  int begin[kMaxRouteDests + 1];
+  int n;
+};
+
+template <bool kRouted>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 project_tc2_kernel(const __grid_constant__ CUtensorMap tmap_phase, const __grid_constant__ CUtensorMap tmap_traj,
-                   const int32_t* __restrict__ expo, float* __restrict__ P, int rows, int n_t, int64_t expo_stride,
-                   int64_t ldp, int a_begin, int a_end, int accumulate, int r_tiles, int t_tiles) {
+                   const int32_t* __restrict__ expo, float* __restrict__ P, const __grid_constant__ RowRoute route,
+                   int rows, int n_t, int64_t expo_stride, int64_t ldp, int a_begin, int a_end, int accumulate,
+                   int r_tiles, int t_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -304,12 +315,26 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tmap_phase, const __grid_
         for (int ch = 0; ch < EPI_COLS / 16; ++ch) {
           const int row0 = tc.row0 + c_begin + ch * 16;
           if (c_begin + ch * 16 < c_end) {
-            float* dst = P + ((int64_t)row0 * 3 + tc.pol) * ldp + t;
+            if constexpr (!kRouted) {
+              float* dst = P + ((int64_t)row0 * 3 + tc.pol) * ldp + t;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (row0 + i < rows) {
-                float* d = dst + (int64_t)i * 3 * ldp;
-                *d = accumulate ? __fadd_rn(*d, v[ch * 16 + i]) : v[ch * 16 + i];
+              for (int i = 0; i < 16; ++i) {
+                if (row0 + i < rows) {
+                  float* d = dst + (int64_t)i * 3 * ldp;
+                  *d = accumulate ? __fadd_rn(*d, v[ch * 16 + i]) : v[ch * 16 + i];
+                }
+              }
+            } else {                                           // per-row destination (warp-uniform lookups)
+              int q = 0;
+              while (q + 1 < route.n && row0 >= route.begin[q + 1]) ++q;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int row = row0 + i;
+                if (row < rows) {
+                  while (q + 1 < route.n && row >= route.begin[q + 1]) ++q;
+                  float* d = route.base[q] + ((int64_t)(row - route.begin[q]) * 3 + tc.pol) * ldp + t;
+                  *d = accumulate ? __fadd_rn(*d, v[ch * 16 + i]) : v[ch * 16 + i];
+                }
               }
             }
           }
@@ -357,9 +382,24 @@ static int make_map(CUtensorMap* map, const int8_t* base, int64_t n_sel, int64_t
 // bdig / expo / P point at the first frame of the range to project; n_t frames of a trajectory of n_t_total frames
 int launch_project_tc2(const int8_t* adig, int64_t rows, int64_t rows_alloc, const int8_t* bdig,
                        const int32_t* expo, int64_t n_t, int64_t n_t_total, int64_t n_sel, int64_t pitch, float* P,
-                       int64_t ldp, cudaStream_t s) {
+                       int64_t ldp, cudaStream_t s, float* const* dests, const int64_t* row_begin, int n_dest) {
   using namespace tc2;
   if (rows == 0 || n_t == 0) return PSA_OK;
+  RowRoute route;
+  memset(&route, 0, sizeof(route));
+  if (n_dest > 0) {
+    PSA_REQUIRE(n_dest <= kMaxRouteDests && dests != nullptr && row_begin != nullptr,
+                "psa_project_routed: 1 to %d destinations", kMaxRouteDests);
+    PSA_REQUIRE(row_begin[0] == 0 && row_begin[n_dest] == rows, "psa_project_routed: row ranges must cover [0, rows)");
+    for (int q = 0; q < n_dest; ++q) {
+      PSA_REQUIRE(row_begin[q + 1] >= row_begin[q], "psa_project_routed: row ranges must be ascending");
+      PSA_REQUIRE(dests[q] != nullptr || row_begin[q + 1] == row_begin[q], "psa_project_routed: null destination %d", q);
+      route.base[q] = dests[q];
+      route.begin[q] = (int)row_begin[q];
+    }
+    route.begin[n_dest] = (int)rows;
+    route.n = n_dest;
+  }
   DeviceGuard guard(adig);
   PSA_REQUIRE(n_sel > 0, "psa_project: empty atom selection");
   PSA_REQUIRE(rows < (1 << 30) && n_t < (1 << 30) && n_sel < (1 << 30), "psa_project: extent too large");
@@ -370,7 +410,8 @@ int launch_project_tc2(const int8_t* adig, int64_t rows, int64_t rows_alloc, con
   if (st != PSA_OK) return st;
 
   // per device and per context: set on every launch (a process may drive several GPUs from several threads)
-  PSA_CUDA(cudaFuncSetAttribute(project_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  PSA_CUDA(cudaFuncSetAttribute(project_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  PSA_CUDA(cudaFuncSetAttribute(project_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   int dev = 0, sms = 0;
   PSA_CUDA(cudaGetDevice(&dev));
   PSA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -382,8 +423,12 @@ int launch_project_tc2(const int8_t* adig, int64_t rows, int64_t rows_alloc, con
   int pass = 0;
   for (int64_t a0 = 0; a0 < n_sel; a0 += kMaxAtomsPerPass, ++pass) {
     int64_t a1 = a0 + kMaxAtomsPerPass < n_sel ? a0 + kMaxAtomsPerPass : n_sel;
-    project_tc2_kernel<<<2 * clusters, THREADS, SMEM_BYTES, s>>>(map_phase, map_traj, expo, P, (int)rows, (int)n_t, n_t_total, ldp,
-                                                                 (int)a0, (int)a1, pass > 0, r_tiles, t_tiles);
+    if (route.n > 0)
+      project_tc2_kernel<true><<<2 * clusters, THREADS, SMEM_BYTES, s>>>(map_phase, map_traj, expo, P, route, (int)rows, (int)n_t,
+                                                                         n_t_total, ldp, (int)a0, (int)a1, pass > 0, r_tiles, t_tiles);
+    else
+      project_tc2_kernel<false><<<2 * clusters, THREADS, SMEM_BYTES, s>>>(map_phase, map_traj, expo, P, route, (int)rows, (int)n_t,
+                                                                          n_t_total, ldp, (int)a0, (int)a1, pass > 0, r_tiles, t_tiles);
     st = launch_status("project_tc2_kernel");
     if (st != PSA_OK) return st;
   }

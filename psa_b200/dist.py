@@ -503,6 +503,18 @@ def frame_shard_plan(n_k: int, world: int, k_cap: int = FRAME_K_CAP):
     return slices, n_chunks, chunk
 
 
+def routed_chunk_rows(chunk, world: int, j: int) -> Tuple[np.ndarray, List[int]]:
+    """One routed projection launch covers chunk j of EVERY owner: returns the k indices in launch order (owner 0's
+    piece, owner 1's, ...) and ``row_begin`` (``world + 1`` entries): projection rows ``[row_begin[q], row_begin[q + 1])``
+    (two per k-point: cos and sin) belong to owner q and become rows 0.. of its buffer."""
+    pieces = [chunk(q, j) for q in range(world)]
+    order = np.concatenate([np.arange(a, b, dtype=np.int64) for a, b in pieces]) if pieces else np.zeros(0, np.int64)
+    row_begin = [0]
+    for a, b in pieces:
+        row_begin.append(row_begin[-1] + 2 * (b - a))
+    return order, row_begin
+
+
 def _all_agree(ok: bool, device, group=None) -> bool:
     flag = torch.tensor([1 if ok else 0], device=device)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
@@ -651,8 +663,32 @@ def frame_sharded_sed(calc, k_vecs: np.ndarray, proj_groups, complex_out: bool, 
         drained[b] = torch.cuda.Event()
         drained[b].record(copy)
 
+    # One launch per chunk for the k-points of ALL owners (the kernel routes every projection row to the buffer of the
+    # rank that owns it): whole waves of tiles and full-width tiles across owner boundaries.  PSA_B200_FRAMES_ROUTED=0
+    # (or the CUDA-core cross-check kernel) falls back to one launch per owner, rank r starting with owner r.
+    routed = eng.project_impl == _lib.PROJECT_TENSOR and os.environ.get("PSA_B200_FRAMES_ROUTED", "1") != "0"
+    kv_routed: List[Optional[torch.Tensor]] = []
+    if routed:
+        routes = [routed_chunk_rows(chunk, world, j) for j in range(n_chunks)]
+        for order, _ in routes:
+            kv_routed.append(eng.upload_small(np.ascontiguousarray(k_vecs[order], np.float32)) if order.size else None)
+        rows_all = 2 * world * kc
     for j in range(n_chunks):
-        for s in range(world):
+        if routed:
+            order, row_begin = routes[j]
+            begin = (ctypes.c_int64 * (world + 1))(*row_begin)
+            n_all = int(order.size)
+            for g, (idx_dev, n_sel, pitch, dig, expo) in enumerate(entries if n_all else []):
+                adig = adig_bufs.get(pitch)
+                if adig is None:
+                    adig = adig_bufs[pitch] = eng.empty((4, rows_all, pitch), torch.int8)
+                eng.phase_digits(kv_routed[j], mean, idx_dev, n_sel, pitch, rows_all, out=adig)
+                dests = (ctypes.c_void_p * world)(*[bufs.ptrs[j % 3][q] + 4 * (g * group_stride + f0)
+                                                    for q in range(world)])
+                eng._run("psa_project_routed", -(-n_sel // 32768), adig.data_ptr(), 2 * n_all, rows_all, dig.data_ptr(),
+                         expo.data_ptr(), n_loc, n_sel, pitch, ctypes.addressof(dests), ctypes.addressof(begin), world,
+                         ldp, eng.stream(), label="psa_project")
+        for s in range(world if not routed else 0):
             q = (rank + s) % world
             ka, kb = chunk(q, j)
             nk = kb - ka

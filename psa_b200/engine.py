@@ -164,8 +164,9 @@ class Engine:
         staged = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
         return staged.to(self.device, non_blocking=True)
 
-    def _run(self, kernel: str, n_launches: int, *args) -> None:
-        """One C-ABI call; with ``self.profile`` set, bracketed by CUDA events on the launching stream."""
+    def _run(self, kernel: str, n_launches: int, *args, label: Optional[str] = None) -> None:
+        """One C-ABI call; with ``self.profile`` set, bracketed by CUDA events on the launching stream (and booked
+        under ``label`` when a variant entry point should count as the kernel it is a variant of)."""
         self.launches += n_launches
         if self.profile is None:
             _lib.call(kernel, *args)
@@ -175,7 +176,7 @@ class Engine:
         start.record(stream)
         _lib.call(kernel, *args)
         end.record(stream)
-        self.profile.setdefault(kernel, []).append((start, end, n_launches))
+        self.profile.setdefault(label or kernel, []).append((start, end, n_launches))
 
     def mark(self, label: str, stream: Optional["torch.cuda.Stream"] = None) -> None:
         """With ``self.timeline`` set: a timing event on ``stream`` (default: the current one) under ``label``."""

@@ -41,6 +41,18 @@ def test_frame_shard_plan_covers_every_k_once(n_k, world, cap):
     assert np.all(seen == 1)
     for s_ in range(world):
         assert sorted((r + s_) % world for r in range(world)) == list(range(world))
+    # routed launches (one per chunk for all owners): the launch order lists every k once, and the row table hands
+    # owner q exactly the rows of its piece, two per k-point
+    every = []
+    for j in range(n_chunks):
+        order, row_begin = pdist.routed_chunk_rows(chunk, world, j)
+        assert len(row_begin) == world + 1 and row_begin[0] == 0 and row_begin[-1] == 2 * order.size
+        for q in range(world):
+            a, b = chunk(q, j)
+            assert row_begin[q + 1] - row_begin[q] == 2 * (b - a)
+            assert np.array_equal(order[row_begin[q] // 2:row_begin[q + 1] // 2], np.arange(a, b))
+        every.append(order)
+    assert np.array_equal(np.sort(np.concatenate(every)), np.arange(n_k))
 
 
 def _free_port():

@@ -215,6 +215,43 @@ def test_projection_by_frame_ranges_is_bit_identical(eng):
         np.testing.assert_array_equal(P.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("bounds", [(0, 130, 130, 296, 400), (0, 400), (0, 2, 398, 400), (0, 0, 144, 400, 400)])
+def test_projection_routed_by_row_ranges_is_bit_identical(eng, bounds):
+    """psa_project_routed: one launch, every row range stored as rows 0.. of its own destination (here: separate local
+    buffers standing in for the peers' IPC-mapped ones, each at a frame offset inside a wider row) - the bits of the
+    one-destination call.  Boundaries inside a 16-row store group, a 2-row owner and empty owners included."""
+    import ctypes
+    from psa_b200 import _lib
+    rows, n_t, n_sel = 400, 600, 200
+    xa, xb, e = _proj_inputs(np.random.default_rng(len(bounds)), rows, n_t, n_sel)
+    want = M.project(xa, xb, e)
+    pitch = -(-n_sel // 64) * 64
+    ad = np.zeros((4, rows + 6, pitch), np.int8)
+    ad[:, :rows, :n_sel] = M.balanced_digits(xa)
+    bd = np.zeros((3, 4, n_t, pitch), np.int8)
+    for pol in range(3):
+        bd[pol, :, :, :n_sel] = M.balanced_digits(xb[pol])
+    ad_d, bd_d, e_d = dev(eng, ad), dev(eng, bd), dev(eng, e)
+    ldp, f0 = 1024, 212                                             # the owner's row pitch and this rank's first frame
+    n_dest = len(bounds) - 1
+    bufs = [torch.full((max(bounds[q + 1] - bounds[q], 1), 3, ldp), float("nan"), dtype=torch.float32, device=eng.device)
+            for q in range(n_dest)]
+    dests = (ctypes.c_void_p * n_dest)(*[b.data_ptr() + 4 * f0 for b in bufs])
+    begin = (ctypes.c_int64 * (n_dest + 1))(*bounds)
+    _lib.call("psa_project_routed", ad_d.data_ptr(), rows, rows + 6, bd_d.data_ptr(), e_d.data_ptr(), n_t, n_sel, pitch,
+              ctypes.addressof(dests), ctypes.addressof(begin), n_dest, ldp, eng.stream())
+    for q in range(n_dest):
+        got = bufs[q].cpu().numpy()
+        r0, r1 = bounds[q], bounds[q + 1]
+        np.testing.assert_array_equal(got[:r1 - r0, :, f0:f0 + n_t], want[r0:r1])
+        assert np.isnan(got[:, :, :f0]).all() and np.isnan(got[:, :, f0 + n_t:]).all()      # nothing outside the range
+    # a bad table is refused before anything is launched
+    begin_bad = (ctypes.c_int64 * (n_dest + 1))(*([0] * n_dest + [rows - 1]))
+    with pytest.raises(ValueError):
+        _lib.call("psa_project_routed", ad_d.data_ptr(), rows, rows + 6, bd_d.data_ptr(), e_d.data_ptr(), n_t, n_sel, pitch,
+                  ctypes.addressof(dests), ctypes.addressof(begin_bad), n_dest, ldp, eng.stream())
+
+
 def test_first_chunk_follows_an_arrival_schedule(gold_si):
     """Digit planes installed with an arrival schedule (frame ranges + events, as the pipelined multi-GPU exchange does):
     the first k-chunk is projected range by range, later chunks in one launch - same bits as the plain path."""
@@ -763,7 +800,8 @@ def test_displacement_moments_every_load_path(eng, n_t, n_a, gather):
     d = (sel - (mean if idx is None else mean[idx])[None]).astype(np.float64)
     out = torch.zeros(2, dtype=torch.float64, device=eng.device)
     idx_dev = None if idx is None else dev(eng, idx)
-    _lib.call("psa_disp_moments", dev(eng, pos).data_ptr(), dev(eng, mean).data_ptr(),
+    pos_dev, mean_dev = dev(eng, pos), dev(eng, mean)              # named: the buffers must outlive the launch
+    _lib.call("psa_disp_moments", pos_dev.data_ptr(), mean_dev.data_ptr(),
               None if idx is None else idx_dev.data_ptr(), n_t, n_a, n_a if idx is None else idx.size,
               out.data_ptr(), eng.stream())
     s1, s2 = out.cpu().tolist()
