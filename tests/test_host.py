@@ -368,3 +368,25 @@ def test_k_chunk_planning():
         chunks = plan_k_chunks(n_k, 500, hint)
         assert chunks[0][0] == 0 and sum(nk for _, nk in chunks) == n_k
         assert all(b[0] == a[0] + a[1] for a, b in zip(chunks, chunks[1:]))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times next to the GPU arm) runs without a GPU and prints ONE
+    JSON line with the contract's keys; its `config` is the object the GPU arm prints for the same workload."""
+    import json
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parents[1]
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--frames", "256", "--cells", "2",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=str(root))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["higher_is_better"] is True and line["n_gpus"] == 1
+    assert line["metric"].endswith("atoms/sec") and line["unit"] == "k*t*atom/s" and line["value"] > 0
+    assert set(line["config"]) == {"workload", "desc"} and line["config"]["workload"] == "c4"
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "k-points" in cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0
