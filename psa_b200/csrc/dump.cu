@@ -3,15 +3,19 @@
 // Byte-for-byte the format the reference writes (reference: src/psa/io/writer.py:139-228) and its GUI parses
 // back (src/psa/gui/psa_gui.py:1396-1455): per frame `ITEM: TIMESTEP`, atom count, orthogonal (`pp pp pp`) or
 // triclinic (`xy xz yz pp pp pp`) box bounds with 8 decimals, then `id type x y z` with 6 decimals.  The reference
-// issues one Python `write` per atom per frame (6.4 M lines per point on the 64 000-atom config); here frames are
-// formatted by a pool of threads into per-frame buffers and written in order.
+// issues one Python `write` per atom per frame (6.4 M lines per point on the 64 000-atom config); here a pool of threads
+// formats whole frames into per-thread buffers and writes each at its own file offset (pwrite).
 //
 // `%.6f` of a float32 is produced exactly (correctly rounded, ties to even on the exact binary value - what both
 // CPython's and glibc's formatters do) with integer arithmetic: x = m 2^e, so x 10^6 = (m 10^6) / 2^-e is a shift.
+#include <errno.h>
+#include <fcntl.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <unistd.h>
 
+#include <atomic>
 #include <string>
 #include <thread>
 #include <vector>
@@ -67,14 +71,16 @@ inline char* put_fixed6(char* p, float x) {
   return p + 6;
 }
 
-void format_frame(std::string& buf, int64_t i_fr, const std::string& box_txt, const float* xyz, const int32_t* types,
-                  int64_t n_at) {
+// formats one frame into buf (only ever grown: no zero fill per frame) and returns the number of bytes
+size_t format_frame(std::vector<char>& buf, int64_t i_fr, const std::string& box_txt, const float* xyz, const int32_t* types,
+                    int64_t n_at) {
   char head[96];
   const int hn = snprintf(head, sizeof(head), "ITEM: TIMESTEP\n%lld\nITEM: NUMBER OF ATOMS\n%lld\n", (long long)i_fr,
                           (long long)n_at);
   static const char atoms_txt[] = "ITEM: ATOMS id type x y z\n";
-  buf.resize((size_t)hn + box_txt.size() + sizeof(atoms_txt) - 1 + (size_t)n_at * 96);
-  char* p = &buf[0];
+  const size_t need = (size_t)hn + box_txt.size() + sizeof(atoms_txt) - 1 + (size_t)n_at * 96;
+  if (buf.size() < need) buf.resize(need);
+  char* p = buf.data();
   memcpy(p, head, (size_t)hn); p += hn;
   memcpy(p, box_txt.data(), box_txt.size()); p += box_txt.size();
   memcpy(p, atoms_txt, sizeof(atoms_txt) - 1); p += sizeof(atoms_txt) - 1;
@@ -90,7 +96,7 @@ void format_frame(std::string& buf, int64_t i_fr, const std::string& box_txt, co
     }
     *p++ = '\n';
   }
-  buf.resize((size_t)(p - &buf[0]));
+  return (size_t)(p - buf.data());
 }
 
 }  // namespace
@@ -124,8 +130,8 @@ extern "C" int psa_write_dump(const char* path, const float* frames_host, const 
     snprintf(line, sizeof(line), "%.8f %.8f\n", 0.0, (double)yhi); box_txt += line;
     snprintf(line, sizeof(line), "%.8f %.8f\n", 0.0, (double)zhi); box_txt += line;
   }
-  FILE* fh = fopen(path, "wb");
-  if (!fh) {
+  const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+  if (fd < 0) {
     set_error("psa_write_dump: cannot open %s for writing", path);
     return PSA_ERR_BAD_ARG;
   }
@@ -133,21 +139,43 @@ extern "C" int psa_write_dump(const char* path, const float* frames_host, const 
   if (workers < 1) workers = 1;
   if (workers > 64) workers = 64;
   if ((int64_t)workers > n_frames) workers = (int)(n_frames > 0 ? n_frames : 1);
-  std::vector<std::string> bufs((size_t)workers);
-  bool ok = true;
-  for (int64_t f0 = 0; f0 < n_frames && ok; f0 += workers) {
-    const int n_now = (int)((n_frames - f0) < workers ? (n_frames - f0) : workers);
-    std::vector<std::thread> pool;
-    for (int w = 1; w < n_now; ++w)
-      pool.emplace_back(format_frame, std::ref(bufs[(size_t)w]), f0 + w, std::cref(box_txt),
-                        frames_host + (f0 + w) * n_atoms * 3, types_host, n_atoms);
-    format_frame(bufs[0], f0, box_txt, frames_host + f0 * n_atoms * 3, types_host, n_atoms);
-    for (auto& t : pool) t.join();
-    for (int w = 0; w < n_now && ok; ++w)
-      ok = fwrite(bufs[(size_t)w].data(), 1, bufs[(size_t)w].size(), fh) == bufs[(size_t)w].size();
-  }
-  ok = (fclose(fh) == 0) && ok;
-  if (!ok) {
+  // Frames are handed out by a counter; a worker formats its frame into its own buffer, learns the frame's file
+  // offset from its predecessor (offset[f + 1] = offset[f] + size[f] is published as soon as frame f is FORMATTED, so
+  // the chain never waits for a write), and writes the buffer at that offset itself: formatting and writing of
+  // different frames overlap, and the file is the same byte for byte.
+  std::vector<std::atomic<int64_t>> offset((size_t)n_frames + 1);
+  for (auto& o : offset) o.store(-1, std::memory_order_relaxed);
+  offset[0].store(0, std::memory_order_release);
+  std::atomic<int64_t> next{0};
+  std::atomic<bool> ok{true};
+  auto work = [&]() {
+    std::vector<char> buf;
+    for (;;) {
+      const int64_t f = next.fetch_add(1, std::memory_order_relaxed);
+      if (f >= n_frames) break;
+      size_t left = format_frame(buf, f, box_txt, frames_host + f * n_atoms * 3, types_host, n_atoms);
+      int64_t at;
+      while ((at = offset[(size_t)f].load(std::memory_order_acquire)) < 0) std::this_thread::yield();
+      offset[(size_t)f + 1].store(at + (int64_t)left, std::memory_order_release);
+      const char* src = buf.data();
+      while (left > 0 && ok.load(std::memory_order_relaxed)) {
+        const ssize_t n = pwrite(fd, src, left, (off_t)at);
+        if (n < 0) {
+          if (errno == EINTR) continue;
+          ok.store(false, std::memory_order_relaxed);
+          break;
+        }
+        src += n; left -= (size_t)n; at += n;
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int w = 1; w < workers; ++w) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+  const bool closed = close(fd) == 0;
+  const bool all_ok = ok.load() && closed;
+  if (!all_ok) {
     set_error("psa_write_dump: write to %s failed", path);
     return PSA_ERR_CUDA;
   }
