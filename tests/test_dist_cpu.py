@@ -198,3 +198,79 @@ def test_shared_host_array_over_gloo(world):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(all(r) for r in results), results
+
+
+# ------------------------------------------------------------------ frame-sharded SED: the whole data flow, CPU stand-ins
+def _frame_sharded_worker(rank, world, port, n_t, n_k, cap, result_q):
+    """What dist.frame_sharded_sed does, with NumPy standing in for the kernels and a SharedHostArray per owner for
+    its IPC-mapped projection buffer: ordered mean chain, every rank projects ITS frames for all k-points in the
+    routed launch order, rows [row_begin[q], row_begin[q + 1]) go into owner q's buffer at this rank's frame offset,
+    a barrier plays the fence, owners transform their slice."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import psa_oracle as O
+        rng = np.random.default_rng(11)
+        n_a = 9
+        pos = (rng.random((n_t, n_a, 3)) * 12 + rng.standard_normal((n_t, n_a, 3)) * 0.02).astype(np.float32)
+        vel = rng.standard_normal((n_t, n_a, 3)).astype(np.float32)
+        kv = (rng.standard_normal((n_k, 3)) * 0.7).astype(np.float32)
+        bounds = [pdist.shard_range(n_t, r, world) for r in range(world)]
+        f0, f1 = bounds[rank]
+
+        def accumulate(acc, last):
+            out = _seq_sum_f32(acc.numpy().copy(), pos[f0:f1])
+            acc.copy_(torch.from_numpy(out / np.float32(n_t) if last else out))
+
+        mean = pdist.chain_running_sum(torch.zeros((n_a, 3), dtype=torch.float32), accumulate).numpy()
+        slices, n_chunks, chunk = pdist.frame_shard_plan(n_k, world, cap)
+        kc = max(chunk(q, j)[1] - chunk(q, j)[0] for q in range(world) for j in range(n_chunks))
+        k0, k1 = slices[rank]
+        out = np.zeros((n_t, k1 - k0, 3), np.complex128)
+        # one projection buffer per owner: [2 kc rows][3][n_t], row 2 i = Re, 2 i + 1 = Im of the owner's i-th k-point
+        bufs = [pdist.SharedHostArray((2 * kc, 3, n_t), np.float64, src=q, register=False) for q in range(world)]
+        for j in range(n_chunks):
+            order, row_begin = pdist.routed_chunk_rows(chunk, world, j)
+            if order.size:
+                ph = O.phase_table(kv[order], mean).astype(np.complex128)                  # (n_all, n_a)
+                proj = np.einsum("tap,ka->kpt", vel[f0:f1].astype(np.float64), ph)         # this rank's frames, all k
+                rows = np.empty((2 * order.size, 3, f1 - f0))
+                rows[0::2], rows[1::2] = proj.real, proj.imag
+                for q in range(world):
+                    a, b = row_begin[q], row_begin[q + 1]
+                    bufs[q].array[:b - a, :, f0:f1] = rows[a:b]                            # the epilogue's peer stores
+            dist.barrier()                                                                 # the fence of chunk j
+            ka, kb = chunk(rank, j)
+            if kb > ka:
+                mine = bufs[rank].array[:2 * (kb - ka)]
+                z = mine[0::2] + 1j * mine[1::2]                                           # (nk, 3, n_t)
+                out[:, ka - k0:kb - k0] = (np.fft.fft(z, axis=2) / n_t).transpose(2, 0, 1)
+            dist.barrier()                                                                 # buffers free for chunk j + 1
+        ph_all = O.phase_table(kv[k0:k1], mean).astype(np.complex128)
+        want = np.fft.fft(np.einsum("tap,ka->tkp", vel.astype(np.float64), ph_all), axis=0) / n_t
+        ok_mean = bool(np.array_equal(mean, np.mean(pos, axis=0, dtype=np.float32)))
+        scale = max(float(np.abs(want).max()), 1e-30) if want.size else 1.0
+        ok_sed = bool(np.abs(out - want).max() <= 1e-12 * scale) if want.size else True
+        for b in bufs:
+            b.close()
+        result_q.put((ok_mean, ok_sed))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_t,n_k,cap", [(2, 64, 21, 2048), (2, 40, 10, 3), (3, 96, 7, 2), (3, 12, 2, 2048)])
+def test_frame_sharded_data_flow_over_gloo(world, n_t, n_k, cap):
+    """Frames spread over the ranks, k-points owned by the ranks: plan, routed row table, frame offsets and owner layout
+    of dist.frame_sharded_sed reproduce the one-process result (float64 stand-in arithmetic; several chunks per owner,
+    ragged slices, an owner without k-points)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_frame_sharded_worker, args=(r, world, port, n_t, n_k, cap, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(all(r) for r in results), results
